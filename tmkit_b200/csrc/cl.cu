@@ -1,0 +1,764 @@
+/* cl.cu - collision context: device tables, batch images, kernel launches, the C ABI on top.
+ *
+ * Reference call shapes: demo/tmpexec.c:397-421 (aa_rx_cl_create / aa_rx_cl_check /
+ * aa_rx_cl_set_get), :118 (allow_config), :322-325 (aa_rx_sg_tf).  Host code is C-style; it is a
+ * .cu only because it launches kernels.  No CPU fallback: every compute entry point needs a
+ * CUDA device and aborts loudly without one.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "kernels.cuh"
+#include "tile.cuh"
+#include "tmk_internal.h"
+
+using namespace tmk;
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            tmk_die("CUDA error %s at %s:%d: %s (no CPU fallback exists)", cudaGetErrorName(e_), __FILE__, \
+                    __LINE__, cudaGetErrorString(e_));                                               \
+    } while (0)
+
+/* ------------------------------------------------------------------ small device buffer helper */
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void need(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        cap = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&p, cap));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T> static void upload(DBuf &b, const std::vector<T> &v, cudaStream_t s) {
+    b.need(std::max<size_t>(16, v.size() * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+/* ------------------------------------------------------------------ scene-graph device mirror (FK) */
+struct SgDev {
+    DBuf frames, q, rel, ab;
+    size_t n_f = 0;
+};
+
+extern "C" void tmk_dev_sg_release(void *dev) {
+    SgDev *d = (SgDev *)dev;
+    if (!d) return;
+    d->frames.release(); d->q.release(); d->rel.release(); d->ab.release();
+    delete d;
+}
+
+static SgDev *sg_dev(const struct aa_rx_sg *sg) {
+    struct aa_rx_sg *m = (struct aa_rx_sg *)sg; /* cache slot is logically mutable */
+    if (m->dev) return (SgDev *)m->dev;
+    SgDev *d = new SgDev();
+    std::vector<DFrame> fr(sg->n_f);
+    for (size_t i = 0; i < sg->n_f; i++) {
+        memcpy(fr[i].E, sg->E + 7 * i, sizeof(double) * 7);
+        memcpy(fr[i].ax, sg->axis + 3 * i, sizeof(double) * 3);
+        fr[i].off = sg->offset[i];
+        fr[i].parent = sg->parent[i];
+        fr[i].type = sg->type[i];
+        fr[i].qidx = sg->qidx[i];
+        fr[i].pad = 0;
+    }
+    upload(d->frames, fr, 0);
+    d->n_f = sg->n_f;
+    d->q.need(sizeof(double) * (sg->n_q + 1));
+    d->rel.need(sizeof(double) * 7 * (sg->n_f + 1));
+    d->ab.need(sizeof(double) * 7 * (sg->n_f + 1));
+    CK(cudaDeviceSynchronize());
+    m->dev = d;
+    return d;
+}
+
+extern "C" void tmk_dev_fk64(const struct aa_rx_sg *sg, const double *q, double *TF_rel, double *TF_abs) {
+    SgDev *d = sg_dev(sg);
+    if (sg->n_q) CK(cudaMemcpy(d->q.p, q, sizeof(double) * sg->n_q, cudaMemcpyHostToDevice));
+    k_fk_single64<<<1, 32>>>((const DFrame *)d->frames.p, (int)sg->n_f, (const double *)d->q.p, (double *)d->rel.p,
+                             (double *)d->ab.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(TF_rel, d->rel.p, sizeof(double) * 7 * sg->n_f, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(TF_abs, d->ab.p, sizeof(double) * 7 * sg->n_f, cudaMemcpyDeviceToHost));
+}
+
+/* ------------------------------------------------------------------ mesh BVH (host build) */
+struct HostMesh {
+    std::vector<BvhNode> nodes;
+    std::vector<double> tris; /* 9 per triangle, reordered by the tree */
+    double centre[3], brad;
+};
+
+static int bvh_build(HostMesh &hm, std::vector<int> &ids, const std::vector<double> &src, int lo, int hi,
+                     std::vector<double> &out_tris) {
+    int me = (int)hm.nodes.size();
+    hm.nodes.push_back(BvhNode());
+    double bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+    double cl[3] = {INFINITY, INFINITY, INFINITY}, ch[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = lo; k < hi; k++) {
+        const double *t = &src[9 * (size_t)ids[k]];
+        for (int a = 0; a < 3; a++) {
+            double c = (t[a] + t[3 + a] + t[6 + a]) / 3;
+            cl[a] = std::min(cl[a], c); ch[a] = std::max(ch[a], c);
+            for (int v = 0; v < 3; v++) { bl[a] = std::min(bl[a], t[3 * v + a]); bh[a] = std::max(bh[a], t[3 * v + a]); }
+        }
+    }
+    BvhNode nd;
+    for (int a = 0; a < 3; a++) {
+        /* round outward so the float box contains the double one */
+        nd.lo[a] = nextafterf((float)bl[a], -INFINITY);
+        nd.hi[a] = nextafterf((float)bh[a], INFINITY);
+    }
+    if (hi - lo <= 2) {
+        nd.a = (int)(out_tris.size() / 9);
+        nd.b = hi - lo;
+        for (int k = lo; k < hi; k++) out_tris.insert(out_tris.end(), &src[9 * (size_t)ids[k]], &src[9 * (size_t)ids[k]] + 9);
+        hm.nodes[me] = nd;
+        return me;
+    }
+    int ax = 0;
+    if (ch[1] - cl[1] > ch[ax] - cl[ax]) ax = 1;
+    if (ch[2] - cl[2] > ch[ax] - cl[ax]) ax = 2;
+    int mid = (lo + hi) / 2;
+    std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int x, int y) {
+        const double *tx = &src[9 * (size_t)x], *ty = &src[9 * (size_t)y];
+        return tx[ax] + tx[3 + ax] + tx[6 + ax] < ty[ax] + ty[3 + ax] + ty[6 + ax];
+    });
+    int l = bvh_build(hm, ids, src, lo, mid, out_tris);
+    int r = bvh_build(hm, ids, src, mid, hi, out_tris);
+    nd.a = l;
+    nd.b = -r - 1;
+    hm.nodes[me] = nd;
+    return me;
+}
+
+static void mesh_compile(const struct aa_rx_mesh *m, HostMesh &hm) {
+    std::vector<double> src(9 * m->nt);
+    for (size_t t = 0; t < m->nt; t++)
+        for (int v = 0; v < 3; v++)
+            for (int a = 0; a < 3; a++) src[9 * t + 3 * v + a] = (double)m->verts[3 * (size_t)m->idx[3 * t + v] + a];
+    std::vector<int> ids(m->nt);
+    for (size_t t = 0; t < m->nt; t++) ids[t] = (int)t;
+    hm.nodes.clear();
+    hm.tris.clear();
+    bvh_build(hm, ids, src, 0, (int)m->nt, hm.tris);
+    /* bounding sphere: centre of the AABB, radius = farthest vertex */
+    const BvhNode &root = hm.nodes[0];
+    for (int a = 0; a < 3; a++) hm.centre[a] = 0.5 * ((double)root.lo[a] + (double)root.hi[a]);
+    double r2 = 0;
+    for (size_t i = 0; i < hm.tris.size() / 3; i++) {
+        double d2 = 0;
+        for (int a = 0; a < 3; a++) d2 += (hm.tris[3 * i + a] - hm.centre[a]) * (hm.tris[3 * i + a] - hm.centre[a]);
+        r2 = std::max(r2, d2);
+    }
+    hm.brad = sqrt(r2) * (1 + 1e-12);
+}
+
+/* ------------------------------------------------------------------ the collision context */
+struct ImageDev {
+    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs;
+    Image<float> f;
+    Image<double> d;
+    std::vector<uint32_t> h_pairs;
+    std::vector<int> pair_fa, pair_fb; /* frames of each pair (for collision tracking) */
+    std::vector<int> sub;
+    std::vector<double> q_base;
+    uint64_t allow_serial = 0;
+    bool valid = false;
+    TileCfg tile;
+};
+
+struct aa_rx_cl {
+    const struct aa_rx_sg *sg;
+    size_t n_f, n_q, n_g, wpr;
+    uint32_t *allowed; /* own copy */
+    uint64_t allow_serial;
+    cudaStream_t stream;
+
+    /* frame-relative geometry + meshes */
+    std::vector<DGeom<double>> geoms;
+    std::vector<HostMesh> hmesh;
+    DBuf d_geoms, d_nodes, d_trisf, d_trisd, d_meshf, d_meshd;
+
+    /* generic pair list for aa_rx_cl_check */
+    std::vector<uint2> gpairs;
+    DBuf d_gpairs, d_gout, d_tf;
+    uint64_t gpairs_serial;
+
+    ImageDev img;
+
+    /* batch scratch */
+    DBuf d_q, d_q1, d_bits, d_unc, d_cnt, d_first, d_pairhit, d_stats;
+    uint32_t *h_cnt; /* pinned */
+    int track, stats_on;
+    std::vector<uint8_t> last_pairhit;
+    struct tmk_batch_stats stats;
+    int use_tile; /* 1: fused tile kernel (default), 0: thread-per-configuration kernel */
+};
+
+static void build_geoms(struct aa_rx_cl *cl) {
+    const struct aa_rx_sg *sg = cl->sg;
+    cl->hmesh.resize(sg->n_mesh);
+    for (size_t m = 0; m < sg->n_mesh; m++) mesh_compile(sg->meshes[m], cl->hmesh[m]);
+    cl->geoms.resize(sg->n_g);
+    for (size_t g = 0; g < sg->n_g; g++) {
+        DGeom<double> &G = cl->geoms[g];
+        memset(&G, 0, sizeof(G));
+        G.tf[3] = 1;
+        G.shape = sg->g_shape[g];
+        G.frame = sg->g_frame[g];
+        G.slot = -1;
+        G.mesh = sg->g_mesh[g];
+        const double *dim = sg->g_dim + 3 * g;
+        switch (G.shape) {
+        case TMK_SPHERE: G.dim[0] = dim[0]; G.brad = dim[0]; break;
+        case TMK_BOX:
+            for (int a = 0; a < 3; a++) G.dim[a] = 0.5 * dim[a];
+            G.brad = sqrt(G.dim[0] * G.dim[0] + G.dim[1] * G.dim[1] + G.dim[2] * G.dim[2]);
+            break;
+        case TMK_CYLINDER: /* base at origin, +z: centred core shifted by h/2 */
+            G.dim[0] = dim[1]; G.dim[1] = 0.5 * dim[0];
+            G.tf[6] = 0.5 * dim[0];
+            G.brad = sqrt(G.dim[0] * G.dim[0] + G.dim[1] * G.dim[1]);
+            break;
+        default:
+            for (int a = 0; a < 3; a++) G.dim[a] = cl->hmesh[G.mesh].centre[a];
+            G.brad = cl->hmesh[G.mesh].brad;
+        }
+        G.brad *= (1 + 1e-12);
+    }
+    /* meshes -> device */
+    std::vector<BvhNode> nodes;
+    std::vector<double> trisd;
+    std::vector<float> trisf;
+    std::vector<size_t> noff, toff;
+    for (auto &hm : cl->hmesh) {
+        noff.push_back(nodes.size());
+        toff.push_back(trisd.size());
+        nodes.insert(nodes.end(), hm.nodes.begin(), hm.nodes.end());
+        trisd.insert(trisd.end(), hm.tris.begin(), hm.tris.end());
+    }
+    trisf.assign(trisd.begin(), trisd.end());
+    upload(cl->d_nodes, nodes, cl->stream);
+    upload(cl->d_trisf, trisf, cl->stream);
+    upload(cl->d_trisd, trisd, cl->stream);
+    std::vector<MeshRef<float>> mf(cl->hmesh.size());
+    std::vector<MeshRef<double>> md(cl->hmesh.size());
+    for (size_t m = 0; m < cl->hmesh.size(); m++) {
+        mf[m].nodes = md[m].nodes = (const BvhNode *)cl->d_nodes.p + noff[m];
+        mf[m].tris = (const float *)cl->d_trisf.p + toff[m];
+        md[m].tris = (const double *)cl->d_trisd.p + toff[m];
+        md[m].brad = cl->hmesh[m].brad; mf[m].brad = (float)cl->hmesh[m].brad;
+        md[m].cx = cl->hmesh[m].centre[0]; md[m].cy = cl->hmesh[m].centre[1]; md[m].cz = cl->hmesh[m].centre[2];
+        mf[m].cx = (float)md[m].cx; mf[m].cy = (float)md[m].cy; mf[m].cz = (float)md[m].cz;
+    }
+    upload(cl->d_meshf, mf, cl->stream);
+    upload(cl->d_meshd, md, cl->stream);
+    upload(cl->d_geoms, cl->geoms, cl->stream);
+    CK(cudaStreamSynchronize(cl->stream));
+}
+
+extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
+    if (!sg || !sg->inited) tmk_die("aa_rx_cl_create: scene graph not initialised");
+    if (!sg->cl_inited) tmk_die("aa_rx_cl_create: call aa_rx_sg_cl_init first");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) tmk_die("aa_rx_cl_create: no CUDA device (no CPU fallback exists)");
+    struct aa_rx_cl *cl = new aa_rx_cl();
+    cl->sg = sg;
+    cl->n_f = sg->n_f; cl->n_q = sg->n_q; cl->n_g = sg->n_g; cl->wpr = sg->wpr;
+    cl->allowed = (uint32_t *)malloc(sizeof(uint32_t) * (cl->n_f * cl->wpr + 1));
+    memcpy(cl->allowed, sg->allowed, sizeof(uint32_t) * cl->n_f * cl->wpr);
+    cl->allow_serial = 1;
+    cl->gpairs_serial = 0;
+    cl->track = 0; cl->stats_on = 0;
+    cl->use_tile = getenv("TMK_NO_TILE") ? 0 : 1;
+    memset(&cl->stats, 0, sizeof(cl->stats));
+    CK(cudaStreamCreateWithFlags(&cl->stream, cudaStreamNonBlocking));
+    CK(cudaMallocHost((void **)&cl->h_cnt, 64));
+    build_geoms(cl);
+    return cl;
+}
+
+extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
+    if (!cl) return;
+    cudaStreamSynchronize(cl->stream);
+    DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
+                    &cl->d_gout, &cl->d_tf, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
+                    &cl->d_pairhit, &cl->d_stats, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
+                    &cl->img.sgd, &cl->img.pairs};
+    for (DBuf *b : bufs) b->release();
+    cudaFreeHost(cl->h_cnt);
+    cudaStreamDestroy(cl->stream);
+    free(cl->allowed);
+    delete cl;
+}
+
+extern "C" void aa_rx_cl_allow(struct aa_rx_cl *cl, aa_rx_frame_id i, aa_rx_frame_id j, int allowed) {
+    if (i < 0 || j < 0 || (size_t)i >= cl->n_f || (size_t)j >= cl->n_f) tmk_die("aa_rx_cl_allow: bad frame id");
+    tmk_bit_put(cl->allowed, cl->wpr, (size_t)i, (size_t)j, allowed);
+    tmk_bit_put(cl->allowed, cl->wpr, (size_t)j, (size_t)i, allowed);
+    cl->allow_serial++;
+}
+extern "C" void aa_rx_cl_allow_set(struct aa_rx_cl *cl, const struct aa_rx_cl_set *set) {
+    if (set->n_f != cl->n_f) tmk_die("aa_rx_cl_allow_set: size mismatch");
+    for (size_t k = 0; k < cl->n_f * cl->wpr; k++) cl->allowed[k] |= set->bits[k];
+    cl->allow_serial++;
+}
+extern "C" void aa_rx_cl_allow_name(struct aa_rx_cl *cl, const char *f0, const char *f1, int allowed) {
+    int i = aa_rx_sg_frame_id(cl->sg, f0), j = aa_rx_sg_frame_id(cl->sg, f1);
+    if (i < 0 || j < 0) tmk_die("aa_rx_cl_allow_name: unknown frame `%s' or `%s'", f0, f1);
+    aa_rx_cl_allow(cl, i, j, allowed);
+}
+
+static inline bool pair_live(const struct aa_rx_cl *cl, int fa, int fb) {
+    return fa != fb && !tmk_bit_get(cl->allowed, cl->wpr, (size_t)fa, (size_t)fb);
+}
+
+/* ------------------------------------------------------------------ aa_rx_cl_check */
+static void run_pairs_tf(struct aa_rx_cl *cl, const double *tf_dense, const std::vector<uint2> &pairs, DBuf &d_pairs,
+                         std::vector<uint8_t> &out) {
+    out.assign(pairs.size(), 0);
+    if (pairs.empty()) return;
+    cl->d_tf.need(sizeof(double) * 7 * cl->n_f);
+    CK(cudaMemcpyAsync(cl->d_tf.p, tf_dense, sizeof(double) * 7 * cl->n_f, cudaMemcpyHostToDevice, cl->stream));
+    cl->d_gout.need(pairs.size());
+    int n = (int)pairs.size();
+    k_pairs_tf64<<<(n + 63) / 64, 64, 0, cl->stream>>>((const double *)cl->d_tf.p, (const DGeom<double> *)cl->d_geoms.p,
+                                                        (const uint2 *)d_pairs.p, n,
+                                                        (const MeshRef<double> *)cl->d_meshd.p, (uint8_t *)cl->d_gout.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out.data(), cl->d_gout.p, pairs.size(), cudaMemcpyDeviceToHost, cl->stream));
+    CK(cudaStreamSynchronize(cl->stream));
+}
+
+extern "C" int aa_rx_cl_check(struct aa_rx_cl *cl, size_t n_tf, const double *TF, size_t ldTF,
+                              struct aa_rx_cl_set *set) {
+    if (n_tf < cl->n_f) tmk_die("aa_rx_cl_check: n_tf = %zu < frame count %zu", n_tf, cl->n_f);
+    if (ldTF < 7) tmk_die("aa_rx_cl_check: leading dimension < 7");
+    if (set && set->n_f != cl->n_f) tmk_die("aa_rx_cl_check: collision set size mismatch");
+    if (cl->gpairs_serial != cl->allow_serial) {
+        cl->gpairs.clear();
+        for (size_t i = 0; i < cl->n_g; i++)
+            for (size_t j = i + 1; j < cl->n_g; j++)
+                if (pair_live(cl, cl->geoms[i].frame, cl->geoms[j].frame)) cl->gpairs.push_back(make_uint2((unsigned)i, (unsigned)j));
+        upload(cl->d_gpairs, cl->gpairs, cl->stream);
+        cl->gpairs_serial = cl->allow_serial;
+    }
+    std::vector<double> dense(7 * cl->n_f);
+    for (size_t i = 0; i < cl->n_f; i++) memcpy(&dense[7 * i], TF + i * ldTF, sizeof(double) * 7);
+    std::vector<uint8_t> out;
+    run_pairs_tf(cl, dense.data(), cl->gpairs, cl->d_gpairs, out);
+    int any = 0;
+    for (size_t p = 0; p < out.size(); p++)
+        if (out[p]) {
+            any = 1;
+            if (set) aa_rx_cl_set_set(set, cl->geoms[cl->gpairs[p].x].frame, cl->geoms[cl->gpairs[p].y].frame, 1);
+        }
+    return any;
+}
+
+/* ------------------------------------------------------------------ batch image */
+template <typename T> static void cvt_joint(const DJoint<double> &s, DJoint<T> &d) {
+    for (int k = 0; k < 7; k++) d.E[k] = (T)s.E[k];
+    for (int k = 0; k < 3; k++) d.ax[k] = (T)s.ax[k];
+    d.off = (T)s.off; d.parent = s.parent; d.type = s.type; d.qslot = s.qslot; d.pad = 0;
+}
+template <typename T> static void cvt_geom(const DGeom<double> &s, DGeom<T> &d) {
+    for (int k = 0; k < 7; k++) d.tf[k] = (T)s.tf[k];
+    for (int k = 0; k < 3; k++) d.dim[k] = (T)s.dim[k];
+    d.brad = (T)(s.brad * (1 + 1e-6)); /* bounding radii only ever round up */
+    d.shape = s.shape; d.slot = s.slot; d.frame = s.frame; d.mesh = s.mesh;
+}
+
+static int pair_class(int sa, int sb) {
+    if (sa == TMK_MESH || sb == TMK_MESH) return PC_MESH;
+    if (sa == TMK_SPHERE || sb == TMK_SPHERE) return PC_CLOSED;
+    if (sa == TMK_BOX && sb == TMK_BOX) return PC_SAT;
+    return PC_GJK;
+}
+
+static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_id *sub_ids, size_t n_q,
+                         const double *q_base) {
+    const struct aa_rx_sg *sg = cl->sg;
+    ImageDev &im = cl->img;
+    if (n_q != cl->n_q) tmk_die("batch: n_q = %zu, scene graph has %zu", n_q, cl->n_q);
+    if (n_sub < 1 || n_sub > TMK_MAXSUB) tmk_die("batch: n_sub = %zu outside 1..%d", n_sub, TMK_MAXSUB);
+    bool same = im.valid && im.allow_serial == cl->allow_serial && im.sub.size() == n_sub &&
+                0 == memcmp(im.sub.data(), sub_ids, sizeof(int) * n_sub) &&
+                0 == memcmp(im.q_base.data(), q_base, sizeof(double) * n_q);
+    if (same) return;
+    for (size_t k = 0; k < n_sub; k++)
+        if (sub_ids[k] < 0 || (size_t)sub_ids[k] >= n_q) tmk_die("batch: bad configuration id %d", sub_ids[k]);
+    im.sub.assign(sub_ids, sub_ids + n_sub);
+    im.q_base.assign(q_base, q_base + n_q);
+    im.allow_serial = cl->allow_serial;
+
+    size_t n_f = cl->n_f;
+    std::vector<double> rel(7 * n_f), ab(7 * n_f);
+    tmk_dev_fk64(sg, q_base, rel.data(), ab.data()); /* static poses come from the GPU FK */
+
+    std::vector<int> slot(n_f, -1), is_joint(n_f, 0);
+    std::vector<double> fold(7 * n_f, 0.0);
+    std::vector<DJoint<double>> joints;
+    for (size_t i = 0; i < n_f; i++) {
+        int p = sg->parent[i];
+        int qs = -1;
+        if (sg->type[i] != TMK_FIXED)
+            for (size_t k = 0; k < n_sub; k++)
+                if (sub_ids[k] == sg->qidx[i]) qs = (int)k;
+        if (qs >= 0) {
+            DJoint<double> J;
+            memset(&J, 0, sizeof(J));
+            const double *E = sg->E + 7 * i;
+            if (p < 0) { memcpy(J.E, E, sizeof(double) * 7); J.parent = -1; }
+            else if (slot[p] < 0) { tmk_tfmul(&ab[7 * p], E, J.E); J.parent = -1; }
+            else { tmk_tfmul(&fold[7 * p], E, J.E); J.parent = slot[p]; }
+            memcpy(J.ax, sg->axis + 3 * i, sizeof(double) * 3);
+            J.off = sg->offset[i];
+            J.type = sg->type[i];
+            J.qslot = qs;
+            slot[i] = (int)joints.size();
+            is_joint[i] = 1;
+            joints.push_back(J);
+            double id7[7] = {0, 0, 0, 1, 0, 0, 0};
+            memcpy(&fold[7 * i], id7, sizeof(id7));
+        } else if (p >= 0 && slot[p] >= 0) {
+            slot[i] = slot[p];
+            tmk_tfmul(&fold[7 * p], &rel[7 * i], &fold[7 * i]);
+        }
+    }
+    if (joints.empty()) tmk_die("batch: none of the sub-configuration variables moves a frame");
+    if (joints.size() > TMK_MAXJ) tmk_die("batch: %zu moving joints > %d", joints.size(), TMK_MAXJ);
+
+    std::vector<DGeom<double>> mg, sgv;
+    std::vector<int> g2m(cl->n_g, -1), g2s(cl->n_g, -1);
+    for (size_t g = 0; g < cl->n_g; g++) {
+        DGeom<double> G = cl->geoms[g];
+        int f = G.frame;
+        double L[7];
+        memcpy(L, G.tf, sizeof(L));
+        if (slot[f] >= 0) {
+            tmk_tfmul(&fold[7 * f], L, G.tf);
+            G.slot = slot[f];
+            g2m[g] = (int)mg.size();
+            mg.push_back(G);
+        } else {
+            tmk_tfmul(&ab[7 * f], L, G.tf);
+            G.slot = -1;
+            g2s[g] = (int)sgv.size();
+            sgv.push_back(G);
+        }
+    }
+    if (mg.size() > TMK_MAXMG) tmk_die("batch: %zu moving geometries > %d", mg.size(), TMK_MAXMG);
+    if (sgv.size() > 65535) tmk_die("batch: too many static geometries");
+
+    /* candidate pairs: every (moving, other) pair that is not same-frame / allowed */
+    struct P { uint32_t w; int fa, fb; };
+    std::vector<P> pairs;
+    for (size_t a = 0; a < cl->n_g; a++) {
+        if (g2m[a] < 0) continue;
+        for (size_t b = 0; b < cl->n_g; b++) {
+            if (b == a || (g2m[b] >= 0 && b < a)) continue;
+            int fa = cl->geoms[a].frame, fb = cl->geoms[b].frame;
+            if (!pair_live(cl, fa, fb)) continue;
+            int cls = pair_class(cl->geoms[a].shape, cl->geoms[b].shape);
+            P p;
+            p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls) : pair_pack(g2m[a], g2s[b], 1, cls);
+            p.fa = fa; p.fb = fb;
+            pairs.push_back(p);
+        }
+    }
+    std::stable_sort(pairs.begin(), pairs.end(), [](const P &x, const P &y) { return (x.w >> 28) < (y.w >> 28); });
+    im.h_pairs.clear(); im.pair_fa.clear(); im.pair_fb.clear();
+    for (auto &p : pairs) { im.h_pairs.push_back(p.w); im.pair_fa.push_back(p.fa); im.pair_fb.push_back(p.fb); }
+
+    /* hoisted static-static pairs, evaluated once (double) */
+    std::vector<uint2> sp;
+    for (size_t a = 0; a < cl->n_g; a++)
+        for (size_t b = a + 1; b < cl->n_g; b++)
+            if (g2m[a] < 0 && g2m[b] < 0 && pair_live(cl, cl->geoms[a].frame, cl->geoms[b].frame))
+                sp.push_back(make_uint2((unsigned)a, (unsigned)b));
+    int static_hit = 0;
+    if (!sp.empty()) {
+        DBuf tmp;
+        upload(tmp, sp, cl->stream);
+        std::vector<uint8_t> out;
+        run_pairs_tf(cl, ab.data(), sp, tmp, out);
+        for (uint8_t o : out) static_hit |= o;
+        tmp.release();
+    }
+
+    std::vector<DJoint<float>> jf(joints.size());
+    for (size_t k = 0; k < joints.size(); k++) cvt_joint(joints[k], jf[k]);
+    std::vector<DGeom<float>> mgf(mg.size()), sgf(sgv.size());
+    for (size_t k = 0; k < mg.size(); k++) cvt_geom(mg[k], mgf[k]);
+    for (size_t k = 0; k < sgv.size(); k++) cvt_geom(sgv[k], sgf[k]);
+    upload(im.jd, joints, cl->stream); upload(im.jf, jf, cl->stream);
+    upload(im.mgd, mg, cl->stream); upload(im.mgf, mgf, cl->stream);
+    upload(im.sgd, sgv, cl->stream); upload(im.sgf, sgf, cl->stream);
+    upload(im.pairs, im.h_pairs, cl->stream);
+    CK(cudaStreamSynchronize(cl->stream));
+
+    im.d.joints = (const DJoint<double> *)im.jd.p; im.f.joints = (const DJoint<float> *)im.jf.p;
+    im.d.mg = (const DGeom<double> *)im.mgd.p; im.f.mg = (const DGeom<float> *)im.mgf.p;
+    im.d.sg = (const DGeom<double> *)im.sgd.p; im.f.sg = (const DGeom<float> *)im.sgf.p;
+    im.d.pairs = im.f.pairs = (const uint32_t *)im.pairs.p;
+    im.d.meshes = (const MeshRef<double> *)cl->d_meshd.p; im.f.meshes = (const MeshRef<float> *)cl->d_meshf.p;
+    im.d.n_joint = im.f.n_joint = (int)joints.size();
+    im.d.n_mg = im.f.n_mg = (int)mg.size();
+    im.d.n_sg = im.f.n_sg = (int)sgv.size();
+    im.d.n_pair = im.f.n_pair = (int)im.h_pairs.size();
+    im.d.n_sub = im.f.n_sub = (int)n_sub;
+    im.d.static_hit = im.f.static_hit = static_hit;
+    tile_configure(im.tile, im.f);
+    im.valid = true;
+}
+
+/* ------------------------------------------------------------------ batch launches */
+static void stats_begin(struct aa_rx_cl *cl) {
+    memset(&cl->stats, 0, sizeof(cl->stats));
+    if (cl->stats_on) {
+        cl->d_stats.need(sizeof(DevStats));
+        CK(cudaMemsetAsync(cl->d_stats.p, 0, sizeof(DevStats), cl->stream));
+    }
+}
+
+static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, int layout, size_t ld,
+                           uint32_t *d_bits, cudaStream_t s) {
+    ImageDev &im = cl->img;
+    QSrc qs;
+    qs.p = dQ; qs.p1 = nullptr; qs.layout = layout; qs.ld = ld;
+    cl->d_unc.need(sizeof(uint32_t) * (n_cfg + 32));
+    cl->d_cnt.need(64);
+    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 64, s));
+    uint8_t *pairhit = nullptr;
+    if (cl->track) {
+        cl->d_pairhit.need(im.h_pairs.size() + 16);
+        CK(cudaMemsetAsync(cl->d_pairhit.p, 0, im.h_pairs.size() + 16, s));
+        pairhit = (uint8_t *)cl->d_pairhit.p;
+    }
+    DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
+    if (n_cfg == 0) return;
+    if (cl->use_tile && im.tile.smem > 0 && !pairhit && !st) {
+        tile_launch(im.tile, im.f, qs, n_cfg, d_bits, (uint32_t *)cl->d_unc.p, (uint32_t *)cl->d_cnt.p, s);
+    } else {
+        unsigned grid = (unsigned)((n_cfg + 127) / 128);
+        k_check_cfg<float, false><<<grid, 128, 0, s>>>(im.f, qs, n_cfg, nullptr, nullptr, d_bits, (uint32_t *)cl->d_unc.p,
+                                                       (uint32_t *)cl->d_cnt.p, pairhit, st);
+    }
+    CK(cudaGetLastError());
+    /* exact re-check of the uncertain configurations (device-side count, no host sync) */
+    k_check_cfg<double, true><<<148 * 2, 128, 0, s>>>(im.d, qs, n_cfg, (const uint32_t *)cl->d_unc.p,
+                                                      (const uint32_t *)cl->d_cnt.p, d_bits, nullptr, nullptr, pairhit, st);
+    CK(cudaGetLastError());
+    cl->stats.n_launches += 2;
+}
+
+static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, const void *dQ1, int layout, size_t ld,
+                         double seg_len, uint32_t *d_bits, int32_t *d_first, cudaStream_t s) {
+    ImageDev &im = cl->img;
+    if (!(seg_len > 0)) tmk_die("edges: seg_len must be positive");
+    QSrc qs;
+    qs.p = dQ0; qs.p1 = dQ1; qs.layout = layout; qs.ld = ld;
+    cl->d_unc.need(sizeof(uint32_t) * (n_edge + 32));
+    cl->d_cnt.need(64);
+    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 64, s));
+    DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
+    if (n_edge == 0) return;
+    unsigned grid = (unsigned)((n_edge + 31) / 32);
+    k_check_edges<float><<<grid, 256, 0, s>>>(im.f, qs, n_edge, seg_len, d_bits, d_first, (uint32_t *)cl->d_unc.p,
+                                              (uint32_t *)cl->d_cnt.p, st);
+    CK(cudaGetLastError());
+    k_recheck_edges64<<<148 * 2, 128, 0, s>>>(im.d, qs, seg_len, (const uint32_t *)cl->d_unc.p,
+                                              (const uint32_t *)cl->d_cnt.p, d_bits, d_first, st);
+    CK(cudaGetLastError());
+    cl->stats.n_launches += 2;
+}
+
+static void stats_end(struct aa_rx_cl *cl, size_t n_units, cudaStream_t s) {
+    ImageDev &im = cl->img;
+    CK(cudaMemcpyAsync(cl->h_cnt, cl->d_cnt.p, 4, cudaMemcpyDeviceToHost, s));
+    DevStats hs;
+    memset(&hs, 0, sizeof(hs));
+    if (cl->stats_on) CK(cudaMemcpyAsync(&hs, cl->d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    if (cl->track) {
+        cl->last_pairhit.assign(im.h_pairs.size(), 0);
+        if (!im.h_pairs.empty())
+            CK(cudaMemcpyAsync(cl->last_pairhit.data(), cl->d_pairhit.p, im.h_pairs.size(), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    cl->stats.n_units = n_units;
+    cl->stats.n_states = cl->stats_on ? hs.n_states : n_units;
+    cl->stats.n_joints = (uint64_t)im.f.n_joint;
+    cl->stats.n_moving_geoms = (uint64_t)im.f.n_mg;
+    cl->stats.n_pairs = (uint64_t)im.f.n_pair;
+    for (int k = 0; k < 4; k++) cl->stats.n_narrow[k] = hs.n_narrow[k];
+    cl->stats.n_uncertain = cl->h_cnt[0];
+}
+
+static size_t count_invalid(const uint32_t *bits, size_t n) {
+    size_t valid = 0;
+    for (size_t w = 0; w < (n + 31) / 32; w++) {
+        uint32_t x = bits[w];
+        if (w == n / 32 && (n & 31)) x &= (1u << (n & 31)) - 1;
+        valid += (size_t)__builtin_popcount(x);
+    }
+    return n - valid;
+}
+
+static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                               size_t n_q, const double *q_base, const void *Q, int layout, size_t ldQ,
+                               uint32_t *valid_bits) {
+    if (ldQ < n_sub) tmk_die("batch: ldQ < n_sub");
+    ensure_image(cl, n_sub, sub_ids, n_q, q_base);
+    stats_begin(cl);
+    size_t esz = layout == TMK_Q_ROWS_F64 ? 8 : 4;
+    size_t nw = (n_cfg + 31) / 32;
+    cl->d_q.need(n_cfg * ldQ * esz + 16);
+    cl->d_bits.need(sizeof(uint32_t) * (nw + 1));
+    if (n_cfg) CK(cudaMemcpyAsync(cl->d_q.p, Q, n_cfg * ldQ * esz, cudaMemcpyHostToDevice, cl->stream));
+    launch_configs(cl, n_cfg, cl->d_q.p, layout, ldQ, (uint32_t *)cl->d_bits.p, cl->stream);
+    if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
+    stats_end(cl, n_cfg, cl->stream);
+    size_t bad = count_invalid(valid_bits, n_cfg);
+    cl->stats.n_invalid = bad;
+    return bad;
+}
+
+extern "C" size_t aa_rx_cl_check_batch(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                       size_t n_q, const double *q_all_base, const double *Q_sub, size_t ldQ,
+                                       uint32_t *valid_bits) {
+    return check_batch_host(cl, n_cfg, n_sub, sub_ids, n_q, q_all_base, Q_sub, TMK_Q_ROWS_F64, ldQ, valid_bits);
+}
+extern "C" size_t aa_rx_cl_check_batch_f32(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub,
+                                           const aa_rx_config_id *sub_ids, size_t n_q, const double *q_all_base,
+                                           const float *Q_sub, size_t ldQ, uint32_t *valid_bits) {
+    return check_batch_host(cl, n_cfg, n_sub, sub_ids, n_q, q_all_base, Q_sub, TMK_Q_ROWS_F32, ldQ, valid_bits);
+}
+
+extern "C" size_t aa_rx_cl_check_edges(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                       size_t n_q, const double *q_all_base, const double *Q0, const double *Q1,
+                                       size_t ldQ, double seg_len, uint32_t *valid_bits, int32_t *first_invalid) {
+    if (ldQ < n_sub) tmk_die("edges: ldQ < n_sub");
+    ensure_image(cl, n_sub, sub_ids, n_q, q_all_base);
+    stats_begin(cl);
+    size_t nw = (n_edge + 31) / 32;
+    cl->d_q.need(n_edge * ldQ * 8 + 16);
+    cl->d_q1.need(n_edge * ldQ * 8 + 16);
+    cl->d_bits.need(sizeof(uint32_t) * (nw + 1));
+    if (first_invalid) cl->d_first.need(sizeof(int32_t) * (n_edge + 1));
+    if (n_edge) {
+        CK(cudaMemcpyAsync(cl->d_q.p, Q0, n_edge * ldQ * 8, cudaMemcpyHostToDevice, cl->stream));
+        CK(cudaMemcpyAsync(cl->d_q1.p, Q1, n_edge * ldQ * 8, cudaMemcpyHostToDevice, cl->stream));
+    }
+    launch_edges(cl, n_edge, cl->d_q.p, cl->d_q1.p, TMK_Q_ROWS_F64, ldQ, seg_len, (uint32_t *)cl->d_bits.p,
+                 first_invalid ? (int32_t *)cl->d_first.p : nullptr, cl->stream);
+    if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
+    if (first_invalid && n_edge)
+        CK(cudaMemcpyAsync(first_invalid, cl->d_first.p, sizeof(int32_t) * n_edge, cudaMemcpyDeviceToHost, cl->stream));
+    stats_end(cl, n_edge, cl->stream);
+    size_t bad = count_invalid(valid_bits, n_edge);
+    cl->stats.n_invalid = bad;
+    return bad;
+}
+
+extern "C" void aa_rx_cl_check_batch_dev(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                         size_t n_q, const double *q_all_base, const void *dQ, int layout, size_t ld,
+                                         uint32_t *d_valid_bits, void *stream) {
+    ensure_image(cl, n_sub, sub_ids, n_q, q_all_base);
+    cudaStream_t s = stream ? (cudaStream_t)stream : cl->stream;
+    if (cl->stats_on) { cl->d_stats.need(sizeof(DevStats)); CK(cudaMemsetAsync(cl->d_stats.p, 0, sizeof(DevStats), s)); }
+    cl->stats.n_launches = 0;
+    launch_configs(cl, n_cfg, dQ, layout, ld, d_valid_bits, s);
+}
+
+extern "C" void aa_rx_cl_check_edges_dev(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                         size_t n_q, const double *q_all_base, const void *dQ0, const void *dQ1,
+                                         int layout, size_t ld, double seg_len, uint32_t *d_valid_bits,
+                                         int32_t *d_first_invalid, void *stream) {
+    ensure_image(cl, n_sub, sub_ids, n_q, q_all_base);
+    cudaStream_t s = stream ? (cudaStream_t)stream : cl->stream;
+    if (cl->stats_on) { cl->d_stats.need(sizeof(DevStats)); CK(cudaMemsetAsync(cl->d_stats.p, 0, sizeof(DevStats), s)); }
+    cl->stats.n_launches = 0;
+    launch_edges(cl, n_edge, dQ0, dQ1, layout, ld, seg_len, d_valid_bits, d_first_invalid, s);
+}
+
+extern "C" void aa_rx_cl_sync(struct aa_rx_cl *cl, void *stream) {
+    CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : cl->stream));
+}
+
+extern "C" void aa_rx_cl_track_collisions(struct aa_rx_cl *cl, int enable) { cl->track = enable ? 1 : 0; }
+
+extern "C" void aa_rx_cl_batch_collisions(struct aa_rx_cl *cl, struct aa_rx_cl_set *set) {
+    if (set->n_f != cl->n_f) tmk_die("aa_rx_cl_batch_collisions: size mismatch");
+    ImageDev &im = cl->img;
+    for (size_t p = 0; p < cl->last_pairhit.size() && p < im.pair_fa.size(); p++)
+        if (cl->last_pairhit[p]) aa_rx_cl_set_set(set, im.pair_fa[p], im.pair_fb[p], 1);
+}
+
+extern "C" void aa_rx_cl_stats_enable(struct aa_rx_cl *cl, int enable) { cl->stats_on = enable ? 1 : 0; }
+extern "C" void aa_rx_cl_batch_stats(struct aa_rx_cl *cl, struct tmk_batch_stats *out) { *out = cl->stats; }
+
+/* ------------------------------------------------------------------ K1 standalone: batched FK */
+extern "C" void aa_rx_sg_tf_batch(const struct aa_rx_sg *sg, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                  size_t n_q, const double *q_all_base, const double *Q_sub, size_t ldQ,
+                                  size_t n_frames, const aa_rx_frame_id *frames, double *TF_abs_out) {
+    if (!sg || !sg->inited) tmk_die("aa_rx_sg_tf_batch: scene graph not initialised");
+    if (n_q != sg->n_q) tmk_die("aa_rx_sg_tf_batch: n_q mismatch");
+    if (ldQ < n_sub) tmk_die("aa_rx_sg_tf_batch: ldQ < n_sub");
+    size_t n_f = sg->n_f;
+    std::vector<FFrame> fr(n_f);
+    size_t n_out = frames ? n_frames : n_f;
+    for (size_t i = 0; i < n_f; i++) {
+        FFrame &F = fr[i];
+        for (int k = 0; k < 7; k++) F.E[k] = (float)sg->E[7 * i + k];
+        for (int k = 0; k < 3; k++) F.ax[k] = (float)sg->axis[3 * i + k];
+        F.off = (float)sg->offset[i];
+        F.parent = sg->parent[i];
+        F.type = sg->type[i];
+        F.qslot = -1;
+        F.qbase = 0;
+        if (F.type) {
+            F.qbase = (float)q_all_base[sg->qidx[i]];
+            for (size_t k = 0; k < n_sub; k++)
+                if (sub_ids[k] == sg->qidx[i]) F.qslot = (int)k;
+        }
+        F.out = frames ? -1 : (int)i;
+    }
+    if (frames)
+        for (size_t k = 0; k < n_frames; k++) {
+            if (frames[k] < 0 || (size_t)frames[k] >= n_f) tmk_die("aa_rx_sg_tf_batch: bad frame id %d", frames[k]);
+            fr[frames[k]].out = (int)k;
+        }
+    if (n_cfg == 0 || n_out == 0) return;
+    const int T = 64;
+    size_t smem = ((sizeof(FFrame) * n_f + 15) & ~(size_t)15) + sizeof(float) * 7 * n_f * T;
+    if (smem > 200 * 1024) tmk_die("aa_rx_sg_tf_batch: %zu frames exceed the shared-memory slab", n_f);
+    DBuf dfr, dq, dout;
+    upload(dfr, fr, 0);
+    dq.need(n_cfg * ldQ * 8);
+    CK(cudaMemcpy(dq.p, Q_sub, n_cfg * ldQ * 8, cudaMemcpyHostToDevice));
+    dout.need(n_cfg * n_out * 7 * 8);
+    CK(cudaFuncSetAttribute(k_fk_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fk_batch<<<(unsigned)((n_cfg + T - 1) / T), T, smem>>>((const FFrame *)dfr.p, (int)n_f, (const double *)dq.p, ldQ,
+                                                             n_cfg, (int)n_out, (double *)dout.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(TF_abs_out, dout.p, n_cfg * n_out * 7 * 8, cudaMemcpyDeviceToHost));
+    dfr.release(); dq.release(); dout.release();
+}
