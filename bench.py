@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark: collision-checked configurations / s (BASELINE.json configs[1]).
+
+A step = one pass of the validity check (FK + broadphase + narrowphase + exact re-check of the
+contact band) over one batch of 2^20 random Baxter right-arm configurations against the Sussman
+block scene.  `value` is measured with the inputs resident in HBM; `e2e` goes through the
+host-buffer C-ABI call (aa_rx_cl_check_batch) with the H2D / D2H copies inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload configs|edges]
+
+N > 1 is launched by torchrun (one rank per GPU); every rank checks its own batch (weak scaling)
+and the validity bitmaps are all-gathered over NCCL inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CFG = 1 << 20
+N_EDGE = 100_000
+RING = 8  # distinct input batches cycled through (RING * batch bytes > L2)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler:
+    """SM clock / throttle-reason samples taken DURING the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [x.strip() for x in line.split(",")]
+            self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample_nvml() if self.nvml else self._sample_smi()
+            except Exception:
+                pass
+            self._stop.wait(0.005 if self.nvml else 0.1)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        self.t.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
+
+
+def flops_per_config(st, n_joint_rev):
+    """F = 61 N_mov + 34 N_rev + 33 G_mov + 11 P + sum_t C_t n_t (n_t measured)."""
+    n = max(1, st.n_states)
+    C = (54.0, 300.0, 1000.0, 250.0)  # closed forms (mean of 48/60), box-box SAT, GJK pair, mesh leaf
+    narrow = sum(C[k] * st.n_narrow[k] for k in range(4)) / n
+    return 61.0 * st.n_joints + 34.0 * n_joint_rev + 33.0 * st.n_moving_geoms + 11.0 * st.n_pairs + narrow
+
+
+def make_problem():
+    from tmkit_b200 import amino as A
+    from tmkit_b200 import scenes as S
+    from tmkit_b200 import workloads as W
+    sc = S.baxter_sussman()
+    return sc, S, W, A
+
+
+def cpu_baseline(workload: str, seconds_budget: float = 12.0):
+    """The CPU restatement (oracle, early-out mode = aa_rx_cl_check with a NULL set) on all host
+    cores, on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    sc, S, W, _ = make_problem()
+    so = "/tmp/libtmkoracle_native.so"
+    try:
+        path = O.build(force=True, march_native=True, out=so)
+    except Exception:
+        path = O.build()
+    flat = S.flatten(sc)
+    orc = O.OracleScene(flat, libpath=path)
+    q0 = np.asarray([S.Q0.get(n, 0.0) for n in orc.config_names])
+    orc.allow_config(q0)
+    sub = orc.config_ids(S.RIGHT_ARM)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    cores = os.cpu_count() or 1
+    if workload == "edges":
+        n = 2000
+        a, b = W.random_edges(lim, n, seed=0)
+        t0 = time.perf_counter()
+        orc.check_edges(sub, q0, a, b, W.seg_len(lim), early_out=True, threads=cores)
+        dt = time.perf_counter() - t0
+        n2 = int(min(200_000, max(n, n * seconds_budget / max(dt, 1e-6))))
+        a, b = W.random_edges(lim, n2, seed=1)
+        t0 = time.perf_counter()
+        orc.check_edges(sub, q0, a, b, W.seg_len(lim), early_out=True, threads=cores)
+        dt = time.perf_counter() - t0
+        return n2 / dt, cores, f"{n2} of {N_EDGE} RRT-like edges, early-out, all cores", n2, dt
+    n = 20000
+    Q = W.random_configs(lim, n, seed=0)
+    t0 = time.perf_counter()
+    orc.check_batch(sub, q0, Q, early_out=True, threads=cores)
+    dt = time.perf_counter() - t0
+    n2 = int(min(4_000_000, max(n, n * seconds_budget / max(dt, 1e-6))))
+    Q = W.random_configs(lim, n2, seed=1)
+    t0 = time.perf_counter()
+    orc.check_batch(sub, q0, Q, early_out=True, threads=cores)
+    dt = time.perf_counter() - t0
+    return n2 / dt, cores, f"{n2} of {N_CFG} configurations, early-out, all cores", n2, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    unit = "configs/s" if args.workload == "configs" else "edges/s"
+    vals = []
+    sample = ""
+    cores = 1
+    for _ in range(max(1, min(args.steps, 3))):
+        v, cores, sample, n, dt = cpu_baseline(args.workload, seconds_budget=8.0)
+        vals.append(v)
+    v = float(np.median(vals))
+    line = {
+        "impl": "reference", "metric": metric_name(args.workload), "value": v, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.workload),
+        "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of Amino/FCL semantics (the reference's Amino/FCL/OMPL are not in the tree)",
+    }
+    print(json.dumps(line))
+
+
+def metric_name(workload):
+    return ("collision-checked configs/sec (FK + collision, Baxter right arm vs Sussman scene)" if workload == "configs"
+            else "swept-edge checks/sec (RRT-Connect segments at OMPL resolution)")
+
+
+def config_dict(workload):
+    if workload == "configs":
+        return {"workload": "BASELINE configs[1]: 2^20 random Baxter 7-DOF right-arm configurations vs the Sussman "
+                            "block scene (restated Baxter fixture), per GPU",
+                "units_per_step_per_gpu": N_CFG, "l2": f"inputs rotate over a ring of {RING} batches (> L2)"}
+    return {"workload": "BASELINE configs[2]: 100K random RRT-like Baxter right-arm segments, OMPL 1% resolution, per GPU",
+            "units_per_step_per_gpu": N_EDGE, "l2": f"inputs rotate over a ring of {RING} batches"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="configs", choices=["configs", "edges"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the validity check has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    sc, S, W, A = make_problem()
+    sg = A.SceneGraph.from_scene(sc)
+    q0 = np.asarray([S.Q0.get(n, 0.0) for n in sg.config_names()])
+    sg.allow_config(q0)  # the reference allows what collides at the start configuration
+    cl = A.Collision(sg)
+    sub = sg.config_indices(S.RIGHT_ARM)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    seg = W.seg_len(lim)
+    edges = args.workload == "edges"
+    n_units = N_EDGE if edges else N_CFG
+    unit = "edges/s" if edges else "configs/s"
+    nw = (n_units + 31) // 32
+
+    # ---- inputs: a ring of distinct batches, SoA float32 in HBM (device-resident leg) ----
+    ring, ring1 = [], []
+    host_rows, host_rows1 = [], []
+    for r in range(RING):
+        seed = 1000 * rank + r
+        if edges:
+            a, b = W.random_edges(lim, n_units, seed=seed)
+            ring.append(torch.from_numpy(np.ascontiguousarray(a.T.astype(np.float32))).to(dev))
+            ring1.append(torch.from_numpy(np.ascontiguousarray(b.T.astype(np.float32))).to(dev))
+            if r < 2:
+                host_rows.append(torch.from_numpy(a).pin_memory()); host_rows1.append(torch.from_numpy(b).pin_memory())
+        else:
+            Q = W.random_configs(lim, n_units, seed=seed)
+            ring.append(torch.from_numpy(np.ascontiguousarray(Q.T.astype(np.float32))).to(dev))
+            if r < 2:
+                host_rows.append(torch.from_numpy(Q).pin_memory())
+    bits = torch.zeros(nw, dtype=torch.int32, device=dev)
+    gathered = torch.zeros(nw * world, dtype=torch.int32, device=dev) if world > 1 else None
+    # a dedicated stream: the C ABI takes a cudaStream_t (NULL would mean the handle's own stream),
+    # and the events below must be recorded on the stream the kernels are launched on
+    ts = torch.cuda.Stream(device=dev)
+    stream = ts.cuda_stream
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(i):
+        k = i % RING
+        if edges:
+            cl.check_edges_dev(n_units, sub, q0, ring[k].data_ptr(), ring1[k].data_ptr(), A.Q_SOA_F32, n_units, seg,
+                               bits.data_ptr(), 0, stream)
+        else:
+            cl.check_batch_dev(n_units, sub, q0, ring[k].data_ptr(), A.Q_SOA_F32, n_units, bits.data_ptr(), stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, bits)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(ts):
+        l2_flush.zero_()
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        cl.kernel_timing(True)  # events around the dominant kernel, recorded by the library on `stream`
+        barrier()
+        ev[0].record(ts)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        ev[1].record(ts)
+        barrier()
+        ms_total = ev[0].elapsed_time(ev[1])
+        n_timed, k_ms_sum, rk_ms_sum = cl.kernel_time()
+        cl.kernel_timing(False)
+        clocks = sampler.stop() if rank == 0 else None
+    assert n_timed == args.steps, (n_timed, args.steps)
+    k_ms = k_ms_sum / n_timed
+    rk_ms = rk_ms_sum / n_timed
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_units * world / (ms_step * 1e-3)
+    valid_frac = float(np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little")[:n_units].mean())
+
+    # ---- e2e: host buffers through the public C-ABI call (H2D + kernels + D2H inside) ----
+    e2e_steps = max(3, min(args.steps, 10))
+    hb = np.zeros(nw + 1, dtype=np.uint32)
+
+    def e2e_step(i):
+        k = i % len(host_rows)
+        if edges:
+            cl.L.aa_rx_cl_check_edges(cl.h, n_units, len(sub), sub.ctypes.data, len(q0), q0.ctypes.data,
+                                      host_rows[k].data_ptr(), host_rows1[k].data_ptr(), len(sub), seg,
+                                      hb.ctypes.data, None)
+        else:
+            cl.L.aa_rx_cl_check_batch(cl.h, n_units, len(sub), sub.ctypes.data, len(q0), q0.ctypes.data,
+                                      host_rows[k].data_ptr(), len(sub), hb.ctypes.data)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)  # blocking: returns with the bitmap in host memory
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_units * world * e2e_steps / float(t.item())
+    h2d = n_units * len(sub) * 8 * (2 if edges else 1)
+    d2h = nw * 4
+
+    # ---- instrumented (untimed) run for the algorithmic flop count ----
+    cl.stats_enable(True)
+    if edges:
+        a, b = W.random_edges(lim, 20000, seed=7)
+        cl.check_edges(sub, q0, a, b, seg, want_first=False)
+    else:
+        cl.check_batch(sub, q0, W.random_configs(lim, 1 << 16, seed=7))
+    st = cl.stats()
+    cl.stats_enable(False)
+    n_rev = int(st.n_joints)
+    f_cfg = flops_per_config(st, n_rev)
+    states_per_unit = st.n_states / max(1, st.n_units)
+    unc_frac = st.n_uncertain / max(1, st.n_units)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_kind, sm_max = load_peaks()
+    bytes_unit = (4 * len(sub) * (2 if edges else 1)) + 1.0 / 8
+    achieved_gbs = bytes_unit * n_units / (k_ms * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+    fp32_probe = cl.L.tmk_fp32_peak_tflops()  # measured on this device: dependent-free FFMA loop, all SMs
+    fp32_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    flops_unit = f_cfg * states_per_unit
+    achieved_tf = flops_unit * n_units / (k_ms * 1e-3) / 1e12
+    kernel = "k_check_edges<float>" if edges else "k_validity_tile"
+
+    line = {
+        "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.workload),
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "aa_rx_cl_check_edges" if edges else "aa_rx_cl_check_batch", "host_dtype": "f64 rows, pinned"},
+        "gpu_launches": int(2 * args.steps),
+        "clocks": clocks,
+        # the path is bound by the FP32 (FMA) pipe, not HBM and not the tensor cores (SURVEY.md 8d,
+        # DESIGN.md): `roofline` is the FP32 one, `roofline_hbm` the contract's HBM form beside it
+        "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_probe, "unit": "TFLOP/s",
+                     "frac": achieved_tf / fp32_probe, "traffic": None, "kernel": kernel, "kernel_ms": k_ms,
+                     "recheck_kernel_ms": rk_ms, "flops_per_unit": flops_unit, "flops_per_state": f_cfg,
+                     "states_per_unit": states_per_unit,
+                     "peak_kind": "measured on this device by tmk_fp32_peak_tflops (FFMA loop)",
+                     "peak_nominal": fp32_nominal},
+        "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind, "kernel": kernel,
+                         "kernel_ms": k_ms, "bytes_per_unit": bytes_unit},
+        "counters": {"joints": int(st.n_joints), "moving_geoms": int(st.n_moving_geoms), "pairs": int(st.n_pairs),
+                     "narrow_per_state": [st.n_narrow[k] / max(1, st.n_states) for k in range(4)],
+                     "uncertain_frac": unc_frac, "valid_frac": valid_frac},
+    }
+    if not args.no_cpu:
+        v, cores, sample, n, dt = cpu_baseline(args.workload)
+        line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+                                "note": "CPU restatement of Amino/FCL semantics (oracle, early-out mode)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -208,6 +208,16 @@ struct tmk_batch_stats {
 void aa_rx_cl_batch_stats(struct aa_rx_cl *cl, struct tmk_batch_stats *out);
 void aa_rx_cl_stats_enable(struct aa_rx_cl *cl, int enable); /* instrumented (slower) runs */
 
+/* Device-time instrumentation for bench.py's roofline: while enabled, CUDA events are recorded on
+ * the launching stream around the main validity kernel and around the double-precision re-check
+ * kernel of every batch.  aa_rx_cl_kernel_time synchronises those events, returns the number of
+ * timed batches, writes the summed device times (ms) and clears the record. */
+void aa_rx_cl_kernel_timing(struct aa_rx_cl *cl, int enable);
+size_t aa_rx_cl_kernel_time(struct aa_rx_cl *cl, double *ms_main, double *ms_recheck);
+
+/* measured FP32 (FFMA) throughput of the current device in TFLOP/s - the FP32 roofline's denominator */
+double tmk_fp32_peak_tflops(void);
+
 const char *tmk_version(void);
 
 #ifdef __cplusplus

@@ -209,7 +209,25 @@ struct aa_rx_cl {
     std::vector<uint8_t> last_pairhit;
     struct tmk_batch_stats stats;
     int use_tile; /* 1: fused tile kernel (default), 0: thread-per-configuration kernel */
+
+    /* device-time instrumentation: events around the main kernel / the re-check kernel of every launch */
+    int timing;
+    std::vector<cudaEvent_t> ev_pool; /* triples: before main, after main, after re-check */
+    size_t ev_used;
 };
+
+static cudaEvent_t *timing_begin(struct aa_rx_cl *cl, cudaStream_t s) {
+    if (!cl->timing) return nullptr;
+    if (cl->ev_used + 3 > cl->ev_pool.size()) {
+        size_t old = cl->ev_pool.size();
+        cl->ev_pool.resize(old + 96);
+        for (size_t k = old; k < cl->ev_pool.size(); k++) CK(cudaEventCreate(&cl->ev_pool[k]));
+    }
+    cudaEvent_t *e = &cl->ev_pool[cl->ev_used];
+    cl->ev_used += 3;
+    CK(cudaEventRecord(e[0], s));
+    return e;
+}
 
 static void build_geoms(struct aa_rx_cl *cl) {
     const struct aa_rx_sg *sg = cl->sg;
@@ -287,6 +305,7 @@ extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
     cl->allow_serial = 1;
     cl->gpairs_serial = 0;
     cl->track = 0; cl->stats_on = 0;
+    cl->timing = 0; cl->ev_used = 0;
     cl->use_tile = getenv("TMK_NO_TILE") ? 0 : 1;
     memset(&cl->stats, 0, sizeof(cl->stats));
     CK(cudaStreamCreateWithFlags(&cl->stream, cudaStreamNonBlocking));
@@ -303,6 +322,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
                     &cl->d_pairhit, &cl->d_stats, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
                     &cl->img.sgd, &cl->img.pairs};
     for (DBuf *b : bufs) b->release();
+    for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     cudaFreeHost(cl->h_cnt);
     cudaStreamDestroy(cl->stream);
     free(cl->allowed);
@@ -555,6 +575,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
     }
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
     if (n_cfg == 0) return;
+    cudaEvent_t *ev = timing_begin(cl, s);
     if (cl->use_tile && im.tile.smem > 0 && !pairhit && !st) {
         tile_launch(im.tile, im.f, qs, n_cfg, d_bits, (uint32_t *)cl->d_unc.p, (uint32_t *)cl->d_cnt.p, s);
     } else {
@@ -563,10 +584,12 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
                                                        (uint32_t *)cl->d_cnt.p, pairhit, st);
     }
     CK(cudaGetLastError());
+    if (ev) CK(cudaEventRecord(ev[1], s));
     /* exact re-check of the uncertain configurations (device-side count, no host sync) */
     k_check_cfg<double, true><<<148 * 2, 128, 0, s>>>(im.d, qs, n_cfg, (const uint32_t *)cl->d_unc.p,
                                                       (const uint32_t *)cl->d_cnt.p, d_bits, nullptr, nullptr, pairhit, st);
     CK(cudaGetLastError());
+    if (ev) CK(cudaEventRecord(ev[2], s));
     cl->stats.n_launches += 2;
 }
 
@@ -581,13 +604,16 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
     CK(cudaMemsetAsync(cl->d_cnt.p, 0, 64, s));
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
     if (n_edge == 0) return;
+    cudaEvent_t *ev = timing_begin(cl, s);
     unsigned grid = (unsigned)((n_edge + 31) / 32);
     k_check_edges<float><<<grid, 256, 0, s>>>(im.f, qs, n_edge, seg_len, d_bits, d_first, (uint32_t *)cl->d_unc.p,
                                               (uint32_t *)cl->d_cnt.p, st);
     CK(cudaGetLastError());
+    if (ev) CK(cudaEventRecord(ev[1], s));
     k_recheck_edges64<<<148 * 2, 128, 0, s>>>(im.d, qs, seg_len, (const uint32_t *)cl->d_unc.p,
                                               (const uint32_t *)cl->d_cnt.p, d_bits, d_first, st);
     CK(cudaGetLastError());
+    if (ev) CK(cudaEventRecord(ev[2], s));
     cl->stats.n_launches += 2;
 }
 
@@ -710,6 +736,70 @@ extern "C" void aa_rx_cl_batch_collisions(struct aa_rx_cl *cl, struct aa_rx_cl_s
     ImageDev &im = cl->img;
     for (size_t p = 0; p < cl->last_pairhit.size() && p < im.pair_fa.size(); p++)
         if (cl->last_pairhit[p]) aa_rx_cl_set_set(set, im.pair_fa[p], im.pair_fb[p], 1);
+}
+
+/* ------------------------------------------------------------------ FP32 roofline probe
+ * The denominator of the FP32 roofline: 8 independent FFMA chains per thread, 8 CTAs of 256 threads
+ * per SM, long enough to reach steady clocks.  Measured, not derived. */
+__global__ void __launch_bounds__(256) k_fma_probe(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456f) out[0] = s; /* never true: keeps the chain alive */
+}
+
+extern "C" double tmk_fp32_peak_tflops(void) {
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *d = nullptr;
+    CK(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int iters = 4096, grid = sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0, 0));
+        k_fma_probe<<<grid, 256>>>(d, iters, 0.999f, 0.001f);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 64.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+}
+
+extern "C" void aa_rx_cl_kernel_timing(struct aa_rx_cl *cl, int enable) {
+    cl->timing = enable ? 1 : 0;
+    cl->ev_used = 0;
+}
+
+extern "C" size_t aa_rx_cl_kernel_time(struct aa_rx_cl *cl, double *ms_main, double *ms_recheck) {
+    size_t n = cl->ev_used / 3;
+    double a = 0, b = 0;
+    for (size_t k = 0; k < n; k++) {
+        cudaEvent_t *e = &cl->ev_pool[3 * k];
+        CK(cudaEventSynchronize(e[2]));
+        float t0 = 0, t1 = 0;
+        CK(cudaEventElapsedTime(&t0, e[0], e[1]));
+        CK(cudaEventElapsedTime(&t1, e[1], e[2]));
+        a += t0; b += t1;
+    }
+    if (ms_main) *ms_main = a;
+    if (ms_recheck) *ms_recheck = b;
+    cl->ev_used = 0;
+    return n;
 }
 
 extern "C" void aa_rx_cl_stats_enable(struct aa_rx_cl *cl, int enable) { cl->stats_on = enable ? 1 : 0; }
