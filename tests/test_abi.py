@@ -167,7 +167,9 @@ def test_scene_plugin_loading(built, tmp_path):
     src = tmp_path / "tiny_scene.c"
     src.write_text(PLUGIN_SRC)
     so = tmp_path / "libtiny_scene.so"
-    subprocess.check_call(["gcc", "-shared", "-fPIC", f"-I{ROOT}/include", "-o", str(so), str(src)])
+    libdir = os.path.dirname(A.LIB_PATH)
+    subprocess.check_call(["gcc", "-shared", "-fPIC", f"-I{ROOT}/include", "-o", str(so), str(src),
+                           f"-L{libdir}", "-l:libtmkcl.so", f"-Wl,-rpath,{libdir}"])  # as Makefile.am links -lamino
     g = A.SceneGraph.dl(str(so), "tiny")
     assert g is not None
     g.init()

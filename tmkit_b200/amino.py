@@ -112,7 +112,8 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: build it (python -c 'import __graft_entry__ as g; g.build()'). "
                                "There is no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
+        # RTLD_GLOBAL: dlopen'ed scene plugins resolve the aa_rx_* constructors against this library
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res
