@@ -238,7 +238,9 @@ static void tile_configure(TileCfg &cfg, const Image<float> &im) {
     cfg.smem = align16(off);
     cfg.grid_max = 0;
     if (cfg.smem > 227 * 1024) { cfg.smem = -1; return; } /* caller falls back to k_check_cfg */
-    cudaFuncSetAttribute(k_validity_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem);
+    /* the attribute is per function, not per context: always raise it to the device maximum so that
+     * images of different sizes (several collision contexts in one process) can coexist */
+    cudaFuncSetAttribute(k_validity_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
