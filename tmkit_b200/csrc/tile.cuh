@@ -240,9 +240,17 @@ static void tile_configure(TileCfg &cfg, const Image<float> &im) {
     if (cfg.smem > 227 * 1024) { cfg.smem = -1; return; } /* caller falls back to k_check_cfg */
     /* the attribute is per function, not per context: always raise it to the device maximum so that
      * images of different sizes (several collision contexts in one process) can coexist */
-    cudaFuncSetAttribute(k_validity_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    int dev = 0, sms = 148, per_sm = 1;
+    int dev = 0, sms = 148, per_sm = 1, optin = 227 * 1024;
     cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_validity_tile) != cudaSuccess) { cfg.smem = -1; return; }
+    int max_dyn = optin - (int)fa.sharedSizeBytes;
+    if (cfg.smem > max_dyn ||
+        cudaFuncSetAttribute(k_validity_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess) {
+        cfg.smem = -1;
+        return;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_validity_tile, TMK_TILE, cfg.smem);
     if (per_sm < 1) per_sm = 1;
