@@ -32,6 +32,17 @@ int h_tri_tri_f64(const double *a, const double *b) {
     return test_tri_tri(mk<double>(a[0], a[1], a[2]), mk<double>(a[3], a[4], a[5]), mk<double>(a[6], a[7], a[8]),
                         mk<double>(b[0], b[1], b[2]), mk<double>(b[3], b[4], b[5]), mk<double>(b[6], b[7], b[8]));
 }
+/* quick certificate of the FP32 broadphase stage: dims in the device convention, brad computed here */
+int h_quick_f32(int sa, const double *da, const double *ta, int sb, const double *db, const double *tb) {
+    auto brad = [](int k, const double *d) {
+        if (k == K_SPHERE) return (float)d[0];
+        if (k == K_BOX) return (float)(sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) * (1 + 1e-6));
+        return (float)(sqrt(d[0] * d[0] + d[1] * d[1]) * (1 + 1e-6));
+    };
+    QG A = qg_make(sa, (float)da[0], (float)da[1], (float)da[2], brad(sa, da), xf_of<float>(ta), mk<float>(0.f, 0.f, 0.f));
+    QG B = qg_make(sb, (float)db[0], (float)db[1], (float)db[2], brad(sb, db), xf_of<float>(tb), mk<float>(0.f, 0.f, 0.f));
+    return quick_pair(sa, A, sb, B);
+}
 int h_ompl_mid(int nd, int k) { return ompl_mid(nd, k); }
 /* FK chain in float vs double: returns the absolute pose of a serial revolute chain */
 void h_fk_chain(int n, const double *E, const double *axis, const double *q, int use_float, double *out) {

@@ -29,6 +29,7 @@ def H(built):
         getattr(L, name).argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     for name in ("h_tri_shape_f32", "h_tri_shape_f64"):
         getattr(L, name).argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    L.h_quick_f32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.h_tri_tri_f64.argtypes = [C.c_void_p, C.c_void_p]
     L.h_ompl_mid.argtypes = [C.c_int, C.c_int]
     L.h_fk_chain.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -107,6 +108,53 @@ def test_convex_pairs_vs_oracle(H, ka, kb):
     assert n_hit > 200 and n_free > 200
     # a third of the cases are constructed within 1e-7..1e-3 m of contact; away from contact UNC must be rare
     assert n_unc < 0.25 * n, n_unc
+
+
+NEED = 3
+
+
+@pytest.mark.parametrize("ka,kb", PAIRS + [(K_CYL, K_BOX), (K_BOX, K_SPHERE), (K_CYL, K_SPHERE)])
+def test_quick_certificates_are_sound(H, ka, kb):
+    """the warp-uniform quick stage (dev_math.cuh quick_pair): SEP never on an oracle HIT, HIT never on
+    an oracle FREE - including flat "table" boxes, thin cylinders and near-contact placements - and
+    it decides most pairs by itself."""
+    rng = np.random.default_rng(1000 + 10 * ka + kb)
+    n = 4000
+    n_decided = n_far = 0
+    for i in range(n):
+        da, sa, oda, fa = _rand_shape(rng, ka)
+        db, sb, odb, fb = _rand_shape(rng, kb)
+        if i % 4 == 1 and kb == K_BOX:  # a table-like slab
+            db = np.array([rng.uniform(0.2, 2.5), rng.uniform(0.2, 2.5), 0.005])
+            odb = 2 * db
+        if i % 4 == 2 and ka == K_BOX:
+            da = np.array([0.005, rng.uniform(0.2, 2.5), rng.uniform(0.2, 2.5)])
+            oda = 2 * da
+        ta, tb = _rand_tf(rng, 0.5), _rand_tf(rng, 0.5)
+        if i % 3 == 0:
+            d = tb[4:] - ta[4:]
+            d /= np.linalg.norm(d) + 1e-30
+            lo, hi = 0.0, 6.0
+            for _ in range(60):
+                mid = 0.5 * (lo + hi)
+                t2 = tb.copy()
+                t2[4:] = ta[4:] + d * mid
+                if O.pair(sa, oda, fa(ta), sb, odb, fb(t2))[1]:
+                    lo = mid
+                else:
+                    hi = mid
+            tb[4:] = ta[4:] + d * (hi + rng.choice([-1, 1]) * 10.0 ** rng.uniform(-7, -2))
+        st, ex = O.pair(sa, oda, fa(ta), sb, odb, fb(tb))
+        r = H.h_quick_f32(ka, da.ctypes.data, ta.ctypes.data, kb, db.ctypes.data, tb.ctypes.data)
+        assert r in (SEP, HIT, UNC, NEED)
+        if r == SEP:
+            assert st != O.HIT, (i, "quick SEP on an oracle HIT")
+        elif r == HIT:
+            assert st != O.FREE, (i, "quick HIT on an oracle FREE")
+        if i % 3 != 0:
+            n_far += 1
+            n_decided += r in (SEP, HIT)
+    assert n_decided > 0.6 * n_far, (n_decided, n_far)
 
 
 @pytest.mark.parametrize("kind", [K_SPHERE, K_BOX, K_CYL])

@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
-#include "tile.cuh"
+#include "warp.cuh"
 #include "tmk_internal.h"
 
 using namespace tmk;
@@ -171,7 +171,7 @@ static void mesh_compile(const struct aa_rx_mesh *m, HostMesh &hm) {
 
 /* ------------------------------------------------------------------ the collision context */
 struct ImageDev {
-    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs;
+    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa;
     Image<float> f;
     Image<double> d;
     std::vector<uint32_t> h_pairs;
@@ -180,7 +180,7 @@ struct ImageDev {
     std::vector<double> q_base;
     uint64_t allow_serial = 0;
     bool valid = false;
-    TileCfg tile;
+    WarpCfg wcfg, wcfg_e;
 };
 
 struct aa_rx_cl {
@@ -203,12 +203,12 @@ struct aa_rx_cl {
     ImageDev img;
 
     /* batch scratch */
-    DBuf d_q, d_q1, d_bits, d_unc, d_cnt, d_first, d_pairhit, d_stats;
+    DBuf d_q, d_q1, d_bits, d_unc, d_cnt, d_first, d_pairhit, d_stats, d_nd, d_alive0, d_alive1, d_efirst;
     uint32_t *h_cnt; /* pinned */
     int track, stats_on;
     std::vector<uint8_t> last_pairhit;
     struct tmk_batch_stats stats;
-    int use_tile; /* 1: fused tile kernel (default), 0: thread-per-configuration kernel */
+    int use_tile; /* 1: warp-pipeline kernel (default), 0: thread-per-configuration kernel */
 
     /* device-time instrumentation: events around the main kernel / the re-check kernel of every launch */
     int timing;
@@ -319,8 +319,8 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     cudaStreamSynchronize(cl->stream);
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
                     &cl->d_gout, &cl->d_tf, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
-                    &cl->d_pairhit, &cl->d_stats, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
-                    &cl->img.sgd, &cl->img.pairs};
+                    &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
+                    &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa};
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     cudaFreeHost(cl->h_cnt);
@@ -397,7 +397,7 @@ extern "C" int aa_rx_cl_check(struct aa_rx_cl *cl, size_t n_tf, const double *TF
 template <typename T> static void cvt_joint(const DJoint<double> &s, DJoint<T> &d) {
     for (int k = 0; k < 7; k++) d.E[k] = (T)s.E[k];
     for (int k = 0; k < 3; k++) d.ax[k] = (T)s.ax[k];
-    d.off = (T)s.off; d.parent = s.parent; d.type = s.type; d.qslot = s.qslot; d.pad = 0;
+    d.off = (T)s.off; d.parent = s.parent; d.type = s.type; d.qslot = s.qslot; d.pad = s.pad;
 }
 template <typename T> static void cvt_geom(const DGeom<double> &s, DGeom<T> &d) {
     for (int k = 0; k < 7; k++) d.tf[k] = (T)s.tf[k];
@@ -466,47 +466,92 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     if (joints.empty()) tmk_die("batch: none of the sub-configuration variables moves a frame");
     if (joints.size() > TMK_MAXJ) tmk_die("batch: %zu moving joints > %d", joints.size(), TMK_MAXJ);
 
+    /* joints whose children do not all follow them directly keep their pose in the joint slab */
+    int n_jslab = 0;
+    for (size_t k = 0; k < joints.size(); k++)
+        if (joints[k].parent >= 0 && joints[k].parent != (int)k - 1 && joints[joints[k].parent].pad == 0)
+            joints[joints[k].parent].pad = ++n_jslab;
+
+    /* moving geometry sorted by joint slot (the kernel walks it joint by joint), static geometry as found */
     std::vector<DGeom<double>> mg, sgv;
     std::vector<int> g2m(cl->n_g, -1), g2s(cl->n_g, -1);
-    for (size_t g = 0; g < cl->n_g; g++) {
-        DGeom<double> G = cl->geoms[g];
-        int f = G.frame;
-        double L[7];
-        memcpy(L, G.tf, sizeof(L));
-        if (slot[f] >= 0) {
+    std::vector<int> jg_begin(joints.size() + 1, 0);
+    for (size_t j = 0; j < joints.size(); j++) {
+        jg_begin[j] = (int)mg.size();
+        for (size_t g = 0; g < cl->n_g; g++) {
+            int f = cl->geoms[g].frame;
+            if (slot[f] != (int)j) continue;
+            DGeom<double> G = cl->geoms[g];
+            double L[7];
+            memcpy(L, G.tf, sizeof(L));
             tmk_tfmul(&fold[7 * f], L, G.tf);
             G.slot = slot[f];
             g2m[g] = (int)mg.size();
             mg.push_back(G);
-        } else {
-            tmk_tfmul(&ab[7 * f], L, G.tf);
-            G.slot = -1;
-            g2s[g] = (int)sgv.size();
-            sgv.push_back(G);
         }
+    }
+    jg_begin[joints.size()] = (int)mg.size();
+    for (size_t g = 0; g < cl->n_g; g++) {
+        int f = cl->geoms[g].frame;
+        if (slot[f] >= 0) continue;
+        DGeom<double> G = cl->geoms[g];
+        double L[7];
+        memcpy(L, G.tf, sizeof(L));
+        tmk_tfmul(&ab[7 * f], L, G.tf);
+        G.slot = -1;
+        g2s[g] = (int)sgv.size();
+        sgv.push_back(G);
     }
     if (mg.size() > TMK_MAXMG) tmk_die("batch: %zu moving geometries > %d", mg.size(), TMK_MAXMG);
     if (sgv.size() > 65535) tmk_die("batch: too many static geometries");
 
-    /* candidate pairs: every (moving, other) pair that is not same-frame / allowed */
-    struct P { uint32_t w; int fa, fb; };
+    /* candidate pairs: every (moving, other) pair that is not same-frame / allowed.  A pair of two
+     * moving geometries is owned by the later one (its partner's pose already exists when the
+     * kernel reaches it).  Grouped by owner, then by narrowphase class. */
+    struct P { uint32_t w; int fa, fb, owner; };
     std::vector<P> pairs;
     for (size_t a = 0; a < cl->n_g; a++) {
         if (g2m[a] < 0) continue;
         for (size_t b = 0; b < cl->n_g; b++) {
-            if (b == a || (g2m[b] >= 0 && b < a)) continue;
+            if (b == a) continue;
+            if (g2m[b] >= 0 && g2m[b] > g2m[a]) continue; /* owned by b */
             int fa = cl->geoms[a].frame, fb = cl->geoms[b].frame;
             if (!pair_live(cl, fa, fb)) continue;
             int cls = pair_class(cl->geoms[a].shape, cl->geoms[b].shape);
             P p;
             p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls) : pair_pack(g2m[a], g2s[b], 1, cls);
-            p.fa = fa; p.fb = fb;
+            p.fa = fa; p.fb = fb; p.owner = g2m[a];
             pairs.push_back(p);
         }
     }
-    std::stable_sort(pairs.begin(), pairs.end(), [](const P &x, const P &y) { return (x.w >> 28) < (y.w >> 28); });
+    std::stable_sort(pairs.begin(), pairs.end(), [](const P &x, const P &y) {
+        if (x.owner != y.owner) return x.owner < y.owner;
+        return (x.w >> 28) < (y.w >> 28);
+    });
+    std::vector<int> pa_begin(mg.size() + 1, 0);
+    for (auto &p : pairs) pa_begin[p.owner + 1]++;
+    for (size_t a = 0; a < mg.size(); a++) pa_begin[a + 1] += pa_begin[a];
     im.h_pairs.clear(); im.pair_fa.clear(); im.pair_fb.clear();
     for (auto &p : pairs) { im.h_pairs.push_back(p.w); im.pair_fa.push_back(p.fa); im.pair_fb.push_back(p.fb); }
+    if (im.h_pairs.size() >= (1u << 27)) tmk_die("batch: too many candidate pairs");
+
+    /* world-frame quick tables of the static geometry */
+    std::vector<SQuick> sq(sgv.size());
+    for (size_t k = 0; k < sgv.size(); k++) {
+        const DGeom<double> &G = sgv[k];
+        SQuick &Q = sq[k];
+        double x = G.tf[0], y = G.tf[1], z = G.tf[2], w = G.tf[3];
+        double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                       2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                       2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        for (int r = 0; r < 3; r++) { Q.a0[r] = (float)R[3 * r]; Q.a1[r] = (float)R[3 * r + 1]; Q.a2[r] = (float)R[3 * r + 2]; }
+        double c[3] = {G.tf[4], G.tf[5], G.tf[6]};
+        if (G.shape == TMK_MESH)
+            for (int r = 0; r < 3; r++) c[r] += R[3 * r] * G.dim[0] + R[3 * r + 1] * G.dim[1] + R[3 * r + 2] * G.dim[2];
+        Q.cx = (float)c[0]; Q.cy = (float)c[1]; Q.cz = (float)c[2];
+        Q.brad = (float)(G.brad * (1 + 1e-6));
+        Q.h0 = (float)G.dim[0]; Q.h1 = (float)G.dim[1]; Q.h2 = (float)G.dim[2];
+    }
 
     /* hoisted static-static pairs, evaluated once (double) */
     std::vector<uint2> sp;
@@ -533,6 +578,9 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     upload(im.mgd, mg, cl->stream); upload(im.mgf, mgf, cl->stream);
     upload(im.sgd, sgv, cl->stream); upload(im.sgf, sgf, cl->stream);
     upload(im.pairs, im.h_pairs, cl->stream);
+    upload(im.sq, sq, cl->stream);
+    upload(im.jg, jg_begin, cl->stream);
+    upload(im.pa, pa_begin, cl->stream);
     CK(cudaStreamSynchronize(cl->stream));
 
     im.d.joints = (const DJoint<double> *)im.jd.p; im.f.joints = (const DJoint<float> *)im.jf.p;
@@ -546,7 +594,11 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     im.d.n_pair = im.f.n_pair = (int)im.h_pairs.size();
     im.d.n_sub = im.f.n_sub = (int)n_sub;
     im.d.static_hit = im.f.static_hit = static_hit;
-    tile_configure(im.tile, im.f);
+    im.d.sq = im.f.sq = im.sq.p;
+    im.d.jg_begin = im.f.jg_begin = (const int *)im.jg.p;
+    im.d.pa_begin = im.f.pa_begin = (const int *)im.pa.p;
+    warp_configure(im.wcfg, im.f, n_jslab, k_states_warp<SrcConfigs, SinkBits>);
+    warp_configure(im.wcfg_e, im.f, n_jslab, k_states_warp<SrcEdgeLevel, SinkEdgeFirst>);
     im.valid = true;
 }
 
@@ -559,14 +611,22 @@ static void stats_begin(struct aa_rx_cl *cl) {
     }
 }
 
+static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
+    UncList u;
+    u.cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states / 2), 0x7fffffffu);
+    cl->d_unc.need(sizeof(uint2) * (size_t)u.cap);
+    cl->d_cnt.need(128);
+    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 128, s));
+    u.items = (uint2 *)cl->d_unc.p;
+    u.n = (uint32_t *)cl->d_cnt.p;
+    u.overflow = (uint32_t *)cl->d_cnt.p + 1;
+    return u;
+}
+
 static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, int layout, size_t ld,
                            uint32_t *d_bits, cudaStream_t s) {
     ImageDev &im = cl->img;
-    QSrc qs;
-    qs.p = dQ; qs.p1 = nullptr; qs.layout = layout; qs.ld = ld;
-    cl->d_unc.need(sizeof(uint32_t) * (n_cfg + 32));
-    cl->d_cnt.need(64);
-    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 64, s));
+    if (n_cfg > 0xfffffff0u) tmk_die("batch: more than 2^32 configurations in one call");
     uint8_t *pairhit = nullptr;
     if (cl->track) {
         cl->d_pairhit.need(im.h_pairs.size() + 16);
@@ -574,15 +634,40 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         pairhit = (uint8_t *)cl->d_pairhit.p;
     }
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
+    if (cl->use_tile && im.wcfg.smem > 0 && !pairhit && !st) {
+        /* fast path: FP32 warp pipelines, then the exact re-check of the undecided pairs */
+        UncList u = unc_list(cl, n_cfg, s);
+        if (n_cfg == 0) return;
+        SrcConfigs src;
+        src.p = dQ; src.layout = layout; src.ld = ld; src.n = n_cfg;
+        SinkBits sink;
+        sink.bits = d_bits;
+        size_t n_groups = (n_cfg + 31) / 32;
+        unsigned grid = (unsigned)std::min<size_t>((n_groups + TMK_WARPS - 1) / TMK_WARPS, (size_t)im.wcfg.grid);
+        cudaEvent_t *ev = timing_begin(cl, s);
+        k_states_warp<SrcConfigs, SinkBits><<<grid, TMK_WARPS * 32, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
+                                                                                        (unsigned long long *)nullptr);
+        CK(cudaGetLastError());
+        if (ev) CK(cudaEventRecord(ev[1], s));
+        k_recheck_items<SrcConfigs, SinkBits><<<148, 128, 0, s>>>(im.d, src, sink, u);
+        CK(cudaGetLastError());
+        k_overflow_all<SrcConfigs, SinkBits><<<148 * 2, 128, 0, s>>>(im.d, src, sink, u);
+        CK(cudaGetLastError());
+        if (ev) CK(cudaEventRecord(ev[2], s));
+        cl->stats.n_launches += 3;
+        return;
+    }
+    /* instrumented path (statistics / collision tracking): one thread per configuration */
+    QSrc qs;
+    qs.p = dQ; qs.p1 = nullptr; qs.layout = layout; qs.ld = ld;
+    cl->d_unc.need(sizeof(uint32_t) * (n_cfg + 32));
+    cl->d_cnt.need(64);
+    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 64, s));
     if (n_cfg == 0) return;
     cudaEvent_t *ev = timing_begin(cl, s);
-    if (cl->use_tile && im.tile.smem > 0 && !pairhit && !st) {
-        tile_launch(im.tile, im.f, qs, n_cfg, d_bits, (uint32_t *)cl->d_unc.p, (uint32_t *)cl->d_cnt.p, s);
-    } else {
-        unsigned grid = (unsigned)((n_cfg + 127) / 128);
-        k_check_cfg<float, false><<<grid, 128, 0, s>>>(im.f, qs, n_cfg, nullptr, nullptr, d_bits, (uint32_t *)cl->d_unc.p,
-                                                       (uint32_t *)cl->d_cnt.p, pairhit, st);
-    }
+    unsigned grid = (unsigned)((n_cfg + 127) / 128);
+    k_check_cfg<float, false><<<grid, 128, 0, s>>>(im.f, qs, n_cfg, nullptr, nullptr, d_bits, (uint32_t *)cl->d_unc.p,
+                                                   (uint32_t *)cl->d_cnt.p, pairhit, st);
     CK(cudaGetLastError());
     if (ev) CK(cudaEventRecord(ev[1], s));
     /* exact re-check of the uncertain configurations (device-side count, no host sync) */
@@ -597,12 +682,64 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
                          double seg_len, uint32_t *d_bits, int32_t *d_first, cudaStream_t s) {
     ImageDev &im = cl->img;
     if (!(seg_len > 0)) tmk_die("edges: seg_len must be positive");
+    if (n_edge > 0x7ffffff0u) tmk_die("edges: more than 2^31 edges in one call");
+    DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
+    if (cl->use_tile && im.wcfg_e.smem > 0 && !st && im.h_pairs.size() < (1u << 19)) {
+        /* fast path: bisection levels through the warp pipelines (warp.cuh) */
+        UncList u = unc_list(cl, n_edge * 4, s);
+        if (n_edge == 0) return;
+        const uint32_t ne = (uint32_t)n_edge;
+        cl->d_nd.need(sizeof(int32_t) * n_edge);
+        cl->d_efirst.need(sizeof(int32_t) * n_edge);
+        cl->d_alive0.need(sizeof(uint32_t) * n_edge);
+        cl->d_alive1.need(sizeof(uint32_t) * n_edge);
+        /* d_cnt: [0] undecided count, [1] overflow, [2..3] evaluated states, [8 + L] alive count of level L */
+        uint32_t *cnt = (uint32_t *)cl->d_cnt.p;
+        int32_t *nd = (int32_t *)cl->d_nd.p, *first = (int32_t *)cl->d_efirst.p;
+        cudaEvent_t *ev = timing_begin(cl, s);
+        k_edges_prep<<<(ne + 255) / 256, 256, 0, s>>>(dQ0, dQ1, layout, ld, im.f.n_sub, ne, seg_len, nd, first,
+                                                      im.f.static_hit);
+        CK(cudaGetLastError());
+        SrcEdgeLevel src;
+        src.p0 = dQ0; src.p1 = dQ1; src.layout = layout; src.ld = ld; src.nd = nd; src.n_edge = ne;
+        SinkEdgeFirst sink;
+        sink.first = first;
+        uint32_t *alive[2] = {(uint32_t *)cl->d_alive0.p, (uint32_t *)cl->d_alive1.p};
+        const uint32_t *cur_alive = nullptr, *cur_n = nullptr;
+        size_t launches = 1;
+        for (int L = 0; L < TMK_EDGE_LEVELS; L++) {
+            src.alive = cur_alive; src.n_alive = cur_n; src.level = L;
+            k_states_warp<SrcEdgeLevel, SinkEdgeFirst><<<im.wcfg_e.grid, TMK_WARPS * 32, im.wcfg_e.smem, s>>>(
+                im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2));
+            CK(cudaGetLastError());
+            launches++;
+            if (L + 1 < TMK_EDGE_LEVELS) {
+                uint32_t *out = alive[L & 1], *n_out = cnt + 8 + L;
+                k_edges_compact<<<148 * 2, 256, 0, s>>>(cur_alive, cur_n, ne, nd, first, L, out, n_out);
+                CK(cudaGetLastError());
+                launches++;
+                cur_alive = out; cur_n = n_out;
+            }
+        }
+        if (ev) CK(cudaEventRecord(ev[1], s));
+        /* undecided (state, pair) items of all levels, in double; positions merge through atomicMin */
+        src.alive = nullptr; src.n_alive = nullptr; src.level = 0;
+        k_recheck_items<SrcEdgeLevel, SinkEdgeFirst><<<148, 128, 0, s>>>(im.d, src, sink, u);
+        CK(cudaGetLastError());
+        k_edges_overflow_all<<<148 * 2, 128, 0, s>>>(im.d, src, u, first);
+        CK(cudaGetLastError());
+        k_edges_finish<<<(ne + 255) / 256, 256, 0, s>>>(first, ne, d_bits, d_first);
+        CK(cudaGetLastError());
+        if (ev) CK(cudaEventRecord(ev[2], s));
+        cl->stats.n_launches += launches + 3;
+        return;
+    }
+    /* instrumented path: one warp per edge */
     QSrc qs;
     qs.p = dQ0; qs.p1 = dQ1; qs.layout = layout; qs.ld = ld;
     cl->d_unc.need(sizeof(uint32_t) * (n_edge + 32));
     cl->d_cnt.need(64);
     CK(cudaMemsetAsync(cl->d_cnt.p, 0, 64, s));
-    DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
     if (n_edge == 0) return;
     cudaEvent_t *ev = timing_begin(cl, s);
     unsigned grid = (unsigned)((n_edge + 31) / 32);
@@ -619,7 +756,7 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
 
 static void stats_end(struct aa_rx_cl *cl, size_t n_units, cudaStream_t s) {
     ImageDev &im = cl->img;
-    CK(cudaMemcpyAsync(cl->h_cnt, cl->d_cnt.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cl->h_cnt, cl->d_cnt.p, 16, cudaMemcpyDeviceToHost, s));
     DevStats hs;
     memset(&hs, 0, sizeof(hs));
     if (cl->stats_on) CK(cudaMemcpyAsync(&hs, cl->d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
@@ -631,6 +768,11 @@ static void stats_end(struct aa_rx_cl *cl, size_t n_units, cudaStream_t s) {
     CK(cudaStreamSynchronize(s));
     cl->stats.n_units = n_units;
     cl->stats.n_states = cl->stats_on ? hs.n_states : n_units;
+    {
+        unsigned long long evaluated = 0; /* the edge pipeline counts the states it evaluates */
+        memcpy(&evaluated, cl->h_cnt + 2, sizeof(evaluated));
+        if (!cl->stats_on && evaluated) cl->stats.n_states = evaluated;
+    }
     cl->stats.n_joints = (uint64_t)im.f.n_joint;
     cl->stats.n_moving_geoms = (uint64_t)im.f.n_mg;
     cl->stats.n_pairs = (uint64_t)im.f.n_pair;

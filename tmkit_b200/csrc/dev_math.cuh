@@ -511,6 +511,126 @@ TMK_HD int test_convex(const Shape<T> &A, const Xf<T> &XA, const Shape<T> &B, co
     return gjk_pair<T>(A.kind, A.a, A.b, (A.kind == K_BOX) ? A.c : T(0), G);
 }
 
+/* ------------------------------------------------------------------ quick certificates (FP32 broadphase stage)
+ * World-frame quick geometry: centre c (bounding centre for meshes), rotation columns x,y,z,
+ * dims (sphere: h0 = r | box: half extents | cylinder: h0 = r, h1 = half height), bounding radius. */
+#define NEED 3 /* quick test: undecided, run the narrowphase */
+struct QG {
+    Vec3<float> c, x, y, z;
+    float h0, h1, h2, brad;
+};
+
+TMK_HD QG qg_make(int kind, float h0, float h1, float h2, float brad, const Xf<float> &X, Vec3<float> mesh_centre) {
+    QG g;
+    Mat3<float> R = q2m(X.r);
+    g.x = mk<float>(R.m00, R.m10, R.m20);
+    g.y = mk<float>(R.m01, R.m11, R.m21);
+    g.z = mk<float>(R.m02, R.m12, R.m22);
+    g.c = X.v;
+    if (kind == K_MESH) g.c = mv(R, mesh_centre) + X.v;
+    g.h0 = h0; g.h1 = h1; g.h2 = h2;
+    g.brad = brad;
+    return g;
+}
+
+/* support radius of a cylinder (axis u, radius r, half height hh) along the unit vector n */
+TMK_HD float cyl_proj(Vec3<float> u, float r, float hh, Vec3<float> n) {
+    Vec3<float> c = cross(n, u);
+    return hh * fabsf(dot(u, n)) + r * sqrtf(dot(c, c));
+}
+TMK_HD float box_proj(const QG &B, Vec3<float> n) {
+    return B.h0 * fabsf(dot(B.x, n)) + B.h1 * fabsf(dot(B.y, n)) + B.h2 * fabsf(dot(B.z, n));
+}
+
+/* Quick verdict of one pair from world-frame quick geometry; ka <= kb is NOT required.
+ * SEP / HIT carry the same certificates as dev_math.cuh (a unit axis with gap > eps; a point of one
+ * shape inside the other by more than eps; closed forms beyond eps).  UNC: a closed form inside
+ * the FP32 allowance.  NEED: undecided, run the full narrowphase. */
+TMK_HD int quick_pair(int ka_in, const QG &A_in, int kb_in, const QG &B_in) {
+    const float eps = Num<float>::eps();
+    {
+        Vec3<float> d0 = B_in.c - A_in.c;
+        float reach = A_in.brad + B_in.brad + eps * 4.0f;
+        if (dot(d0, d0) > reach * reach) return SEP;
+    }
+    if (ka_in == K_MESH || kb_in == K_MESH) return NEED;
+    /* order so that kind(A) <= kind(B) (the pair's shapes are warp-uniform, so is this choice) */
+    const bool sw = ka_in > kb_in;
+    const QG &A = sw ? B_in : A_in;
+    const QG &B = sw ? A_in : B_in;
+    const int ka = sw ? kb_in : ka_in, kb = sw ? ka_in : kb_in;
+    const Vec3<float> d = B.c - A.c;
+    if (ka == K_SPHERE) {
+        if (kb == K_SPHERE) return classify(sqrtf(dot(d, d)) - A.h0 - B.h0);
+        Vec3<float> p = mk<float>(-dot(d, B.x), -dot(d, B.y), -dot(d, B.z)); /* A's centre in B's frame */
+        float dist = (kb == K_BOX) ? point_box(p, B.h0, B.h1, B.h2) : point_cyl(p, B.h0, B.h1);
+        return classify(dist - A.h0);
+    }
+    if (ka == K_BOX && kb == K_BOX) {
+        /* face axes of both boxes */
+        float ta0 = dot(d, A.x), ta1 = dot(d, A.y), ta2 = dot(d, A.z);
+        float g = fabsf(ta0) - A.h0 - box_proj(B, A.x);
+        g = fmaxf(g, fabsf(ta1) - A.h1 - box_proj(B, A.y));
+        g = fmaxf(g, fabsf(ta2) - A.h2 - box_proj(B, A.z));
+        float tb0 = dot(d, B.x), tb1 = dot(d, B.y), tb2 = dot(d, B.z);
+        g = fmaxf(g, fabsf(tb0) - B.h0 - box_proj(A, B.x));
+        g = fmaxf(g, fabsf(tb1) - B.h1 - box_proj(A, B.y));
+        g = fmaxf(g, fabsf(tb2) - B.h2 - box_proj(A, B.z));
+        if (g > eps) return SEP;
+        if (fabsf(ta0) < A.h0 - eps && fabsf(ta1) < A.h1 - eps && fabsf(ta2) < A.h2 - eps) return HIT; /* B's centre in A */
+        if (fabsf(tb0) < B.h0 - eps && fabsf(tb1) < B.h1 - eps && fabsf(tb2) < B.h2 - eps) return HIT; /* A's centre in B */
+        return NEED;
+    }
+    if (ka == K_BOX) { /* box A, cylinder B (axis B.z, radius B.h0, half height B.h1) */
+        float t0 = dot(d, A.x), t1 = dot(d, A.y), t2 = dot(d, A.z);
+        float g = fabsf(t0) - A.h0 - cyl_proj(B.z, B.h0, B.h1, A.x);
+        g = fmaxf(g, fabsf(t1) - A.h1 - cyl_proj(B.z, B.h0, B.h1, A.y));
+        g = fmaxf(g, fabsf(t2) - A.h2 - cyl_proj(B.z, B.h0, B.h1, A.z));
+        float tz = dot(d, B.z);
+        g = fmaxf(g, fabsf(tz) - B.h1 - box_proj(A, B.z));
+        Vec3<float> dp = d - B.z * tz; /* radial direction from the cylinder axis to the box centre */
+        float rho2 = dot(dp, dp);
+        float rho = sqrtf(rho2);
+        if (rho2 > 1e-12f) {
+            Vec3<float> n = dp * (1.0f / rho);
+            g = fmaxf(g, rho - B.h0 - box_proj(A, n));
+        }
+        if (g > eps) return SEP;
+        if (fabsf(t0) < A.h0 - eps && fabsf(t1) < A.h1 - eps && fabsf(t2) < A.h2 - eps) return HIT; /* cyl centre in box */
+        if (fabsf(tz) < B.h1 - eps && rho < B.h0 - eps) return HIT;                                   /* box centre in cyl */
+        return NEED;
+    }
+    /* cylinder - cylinder */
+    {
+        float ta = dot(d, A.z), tb = dot(d, B.z);
+        float g = fabsf(ta) - A.h1 - cyl_proj(B.z, B.h0, B.h1, A.z);
+        g = fmaxf(g, fabsf(tb) - B.h1 - cyl_proj(A.z, A.h0, A.h1, B.z));
+        Vec3<float> n = cross(A.z, B.z);
+        float n2 = dot(n, n);
+        if (n2 > 1e-6f) { /* common perpendicular of the two axes: both cylinders project to their radius */
+            float inv = 1.0f / sqrtf(n2);
+            g = fmaxf(g, fabsf(dot(d, n)) * inv - A.h0 - B.h0);
+        }
+        Vec3<float> da = d - A.z * ta; /* radial direction of A towards B's centre */
+        float ra2 = dot(da, da), ra = sqrtf(ra2);
+        if (ra2 > 1e-12f) {
+            Vec3<float> m = da * (1.0f / ra);
+            g = fmaxf(g, ra - A.h0 - cyl_proj(B.z, B.h0, B.h1, m));
+        }
+        Vec3<float> db = d - B.z * tb;
+        float rb2 = dot(db, db), rb = sqrtf(rb2);
+        if (rb2 > 1e-12f) {
+            Vec3<float> m = db * (1.0f / rb);
+            g = fmaxf(g, rb - B.h0 - cyl_proj(A.z, A.h0, A.h1, m));
+        }
+        if (g > eps) return SEP;
+        if (fabsf(ta) < A.h1 - eps && ra < A.h0 - eps) return HIT; /* B's centre in A */
+        if (fabsf(tb) < B.h1 - eps && rb < B.h0 - eps) return HIT; /* A's centre in B */
+        return NEED;
+    }
+}
+
+
 /* ------------------------------------------------------------------ meshes: AABB tree in mesh-local frame */
 struct BvhNode {
     float lo[3];

@@ -26,7 +26,7 @@ template <typename T> struct DJoint {
     int parent;  /* joint slot or -1 */
     int type;    /* 1 revolute, 2 prismatic */
     int qslot;   /* index into the sub-configuration */
-    int pad;
+    int pad;     /* > 0: slot+1 in the joint-pose slab (joints whose children do not follow them directly) */
 };
 
 template <typename T> struct DGeom {
@@ -51,6 +51,9 @@ template <typename T> struct Image {
     const DGeom<T> *sg;
     const uint32_t *pairs;
     const MeshRef<T> *meshes;
+    const void *sq;      /* SQuick[n_sg]: world-frame quick tables of the static geometry (float image) */
+    const int *jg_begin; /* [n_joint+1]: moving geometries of joint j are mg[jg_begin[j] .. jg_begin[j+1]) */
+    const int *pa_begin; /* [n_mg+1]: pairs owned by moving geometry a are pairs[pa_begin[a] .. pa_begin[a+1]) */
     int n_joint, n_mg, n_sg, n_pair;
     int n_sub;
     int static_hit; /* a non-allowed static-static pair collides: every configuration is invalid */
