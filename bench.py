@@ -335,19 +335,28 @@ def main():
     h2d = n_units * len(sub) * 8 * (2 if edges else 1)
     d2h = nw * 4
 
-    # ---- instrumented (untimed) run for the algorithmic flop count ----
-    cl.stats_enable(True)
+    # ---- untimed runs for the counters: the production path (launches, states it evaluates, pairs it
+    # re-checks in double) and the instrumented path (narrowphase calls by class for the flop formula) ----
     if edges:
         a, b = W.random_edges(lim, 20000, seed=7)
         cl.check_edges(sub, q0, a, b, seg, want_first=False)
     else:
-        cl.check_batch(sub, q0, W.random_configs(lim, 1 << 16, seed=7))
+        Qs = W.random_configs(lim, 1 << 16, seed=7)
+        cl.check_batch(sub, q0, Qs)
+    fast = cl.stats()
+    launches_per_step = int(fast.n_launches)
+    states_per_unit = fast.n_states / max(1, fast.n_units)
+    unc_frac = fast.n_uncertain / max(1, fast.n_states)
+    cl.stats_enable(True)
+    if edges:
+        cl.check_edges(sub, q0, a, b, seg, want_first=False)
+    else:
+        cl.check_batch(sub, q0, Qs)
     st = cl.stats()
     cl.stats_enable(False)
     n_rev = int(st.n_joints)
     f_cfg = flops_per_config(st, n_rev)
-    states_per_unit = st.n_states / max(1, st.n_units)
-    unc_frac = st.n_uncertain / max(1, st.n_units)
+    states_per_unit_ref = st.n_states / max(1, st.n_units)
 
     if rank != 0:
         if world > 1:
@@ -362,7 +371,7 @@ def main():
     fp32_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     flops_unit = f_cfg * states_per_unit
     achieved_tf = flops_unit * n_units / (k_ms * 1e-3) / 1e12
-    kernel = "k_check_edges<float>" if edges else "k_validity_tile"
+    kernel = "k_states_tile<SrcEdgeLevel> (all bisection levels)" if edges else "k_states_tile<SrcConfigs>"
 
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
@@ -371,7 +380,7 @@ def main():
         "config": config_dict(args.workload),
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "aa_rx_cl_check_edges" if edges else "aa_rx_cl_check_batch", "host_dtype": "f64 rows, pinned"},
-        "gpu_launches": int(2 * args.steps),
+        "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
         # the path is bound by the FP32 (FMA) pipe, not HBM and not the tensor cores (SURVEY.md 8d,
         # DESIGN.md): `roofline` is the FP32 one, `roofline_hbm` the contract's HBM form beside it
@@ -386,7 +395,9 @@ def main():
                          "kernel_ms": k_ms, "bytes_per_unit": bytes_unit},
         "counters": {"joints": int(st.n_joints), "moving_geoms": int(st.n_moving_geoms), "pairs": int(st.n_pairs),
                      "narrow_per_state": [st.n_narrow[k] / max(1, st.n_states) for k in range(4)],
-                     "uncertain_frac": unc_frac, "valid_frac": valid_frac},
+                     "states_per_unit_one_warp_per_edge_kernel": states_per_unit_ref,
+                     "double_rechecked_pairs_per_state": unc_frac, "valid_frac": valid_frac,
+                     "kernels_per_step": launches_per_step},
     }
     if not args.no_cpu:
         v, cores, sample, n, dt = cpu_baseline(args.workload)

@@ -5,8 +5,8 @@ set -u
 TAG=${1:-r1}
 WL=${2:-configs}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --workload $WL"
-KREGEX=k_states_warp
-[ "$WL" = edges ] && KREGEX=k_states_warp
+KREGEX=k_states_tile
+[ "$WL" = edges ] && KREGEX=k_states_tile
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_${WL}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \

@@ -180,7 +180,7 @@ struct ImageDev {
     std::vector<double> q_base;
     uint64_t allow_serial = 0;
     bool valid = false;
-    WarpCfg wcfg, wcfg_e;
+    TileCfg wcfg, wcfg_e;
 };
 
 struct aa_rx_cl {
@@ -519,7 +519,8 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
             if (!pair_live(cl, fa, fb)) continue;
             int cls = pair_class(cl->geoms[a].shape, cl->geoms[b].shape);
             P p;
-            p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls) : pair_pack(g2m[a], g2s[b], 1, cls);
+            p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls, cl->geoms[b].shape)
+                              : pair_pack(g2m[a], g2s[b], 1, cls, cl->geoms[b].shape);
             p.fa = fa; p.fb = fb; p.owner = g2m[a];
             pairs.push_back(p);
         }
@@ -544,7 +545,9 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
                        2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
                        2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
-        for (int r = 0; r < 3; r++) { Q.a0[r] = (float)R[3 * r]; Q.a1[r] = (float)R[3 * r + 1]; Q.a2[r] = (float)R[3 * r + 2]; }
+        Q.a0x = (float)R[0]; Q.a0y = (float)R[3]; Q.a0z = (float)R[6];
+        Q.a1x = (float)R[1]; Q.a1y = (float)R[4]; Q.a1z = (float)R[7];
+        Q.a2x = (float)R[2]; Q.a2y = (float)R[5]; Q.a2z = (float)R[8];
         double c[3] = {G.tf[4], G.tf[5], G.tf[6]};
         if (G.shape == TMK_MESH)
             for (int r = 0; r < 3; r++) c[r] += R[3 * r] * G.dim[0] + R[3 * r + 1] * G.dim[1] + R[3 * r + 2] * G.dim[2];
@@ -597,8 +600,10 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     im.d.sq = im.f.sq = im.sq.p;
     im.d.jg_begin = im.f.jg_begin = (const int *)im.jg.p;
     im.d.pa_begin = im.f.pa_begin = (const int *)im.pa.p;
-    warp_configure(im.wcfg, im.f, n_jslab, k_states_warp<SrcConfigs, SinkBits>);
-    warp_configure(im.wcfg_e, im.f, n_jslab, k_states_warp<SrcEdgeLevel, SinkEdgeFirst>);
+    tile_configure(im.wcfg, im.f, n_jslab, k_states_tile<SrcConfigs, SinkBits, 256>, k_states_tile<SrcConfigs, SinkBits, 128>);
+    tile_configure(im.wcfg_e, im.f, n_jslab, k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256>,
+                   k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128>);
+    if (im.h_pairs.size() >= (1u << 20)) im.wcfg.smem = im.wcfg_e.smem = -1; /* queue items hold 20-bit pair indices */
     im.valid = true;
 }
 
@@ -642,11 +647,15 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         src.p = dQ; src.layout = layout; src.ld = ld; src.n = n_cfg;
         SinkBits sink;
         sink.bits = d_bits;
-        size_t n_groups = (n_cfg + 31) / 32;
-        unsigned grid = (unsigned)std::min<size_t>((n_groups + TMK_WARPS - 1) / TMK_WARPS, (size_t)im.wcfg.grid);
+        const int T = im.wcfg.tile;
+        unsigned grid = (unsigned)std::min<size_t>((n_cfg + T - 1) / T, (size_t)im.wcfg.grid);
         cudaEvent_t *ev = timing_begin(cl, s);
-        k_states_warp<SrcConfigs, SinkBits><<<grid, TMK_WARPS * 32, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
-                                                                                        (unsigned long long *)nullptr);
+        if (T == 256)
+            k_states_tile<SrcConfigs, SinkBits, 256><<<grid, 256, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
+                                                                                      (unsigned long long *)nullptr);
+        else
+            k_states_tile<SrcConfigs, SinkBits, 128><<<grid, 128, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
+                                                                                      (unsigned long long *)nullptr);
         CK(cudaGetLastError());
         if (ev) CK(cudaEventRecord(ev[1], s));
         k_recheck_items<SrcConfigs, SinkBits><<<148, 128, 0, s>>>(im.d, src, sink, u);
@@ -709,8 +718,12 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         size_t launches = 1;
         for (int L = 0; L < TMK_EDGE_LEVELS; L++) {
             src.alive = cur_alive; src.n_alive = cur_n; src.level = L;
-            k_states_warp<SrcEdgeLevel, SinkEdgeFirst><<<im.wcfg_e.grid, TMK_WARPS * 32, im.wcfg_e.smem, s>>>(
-                im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2));
+            if (im.wcfg_e.tile == 256)
+                k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256><<<im.wcfg_e.grid, 256, im.wcfg_e.smem, s>>>(
+                    im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2));
+            else
+                k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128><<<im.wcfg_e.grid, 128, im.wcfg_e.smem, s>>>(
+                    im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2));
             CK(cudaGetLastError());
             launches++;
             if (L + 1 < TMK_EDGE_LEVELS) {

@@ -39,9 +39,9 @@ template <typename T> struct DGeom {
     int mesh;
 };
 
-/* pair word: bits 0-7 moving geom a | 8-23 geom b | 24 b is static | 28-31 class */
-__host__ __device__ inline uint32_t pair_pack(int a, int b, int b_static, int cls) {
-    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)b_static << 24) | ((uint32_t)cls << 28);
+/* pair word: bits 0-7 moving geom a | 8-23 geom b | 24 b is static | 25-27 shape of b | 28-31 class */
+__host__ __device__ inline uint32_t pair_pack(int a, int b, int b_static, int cls, int shape_b) {
+    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)b_static << 24) | ((uint32_t)shape_b << 25) | ((uint32_t)cls << 28);
 }
 enum { PC_CLOSED = 0, PC_SAT = 1, PC_GJK = 2, PC_MESH = 3 };
 

@@ -27,21 +27,22 @@
 
 namespace tmk {
 
-#define TMK_WARPS 8
-#define TMK_WQ 384 /* queue entries per warp */
 
 /* world-frame quick geometry: centre, axes (columns of the rotation), dims, bounding radius */
 struct SQuick {
     float cx, cy, cz, brad;
-    float a0[3], a1[3], a2[3];
-    float h0, h1, h2;
+    float a0x, a0y, a0z, h0; /* axis i and the dimension along it share one 16-byte load */
+    float a1x, a1y, a1z, h1;
+    float a2x, a2y, a2z, h2;
 };
 
-struct WarpCfg {
+struct TileCfg {
     int stage; /* 1: image staged in shared memory */
-    int off_joint, off_mg, off_sg, off_pairs, off_sq, off_jg, off_pa, off_warp;
+    int off_joint, off_mg, off_sg, off_pairs, off_sq, off_jg, off_pa;
     int bytes_joint, bytes_mg, bytes_sg, bytes_pairs, bytes_sq, bytes_jg, bytes_pa;
-    int warp_bytes, woff_q, woff_queue, woff_flags, woff_unc, woff_jslab;
+    int off_slab, off_qs, off_jslab, off_q1, off_q2, off_q3, off_flags, off_unc;
+    int q1_cap, q2_cap, q3_cap;
+    int tile; /* threads per CTA = states per pass: 256 or 128 */
     int smem, grid;
 };
 
@@ -60,25 +61,12 @@ __device__ __forceinline__ QG qg_from_pose(const DGeom<float> &G, const Xf<float
 __device__ __forceinline__ QG qg_from_static(const SQuick &s) {
     QG g;
     g.c = mk<float>(s.cx, s.cy, s.cz);
-    g.x = mk<float>(s.a0[0], s.a0[1], s.a0[2]);
-    g.y = mk<float>(s.a1[0], s.a1[1], s.a1[2]);
-    g.z = mk<float>(s.a2[0], s.a2[1], s.a2[2]);
+    g.x = mk<float>(s.a0x, s.a0y, s.a0z);
+    g.y = mk<float>(s.a1x, s.a1y, s.a1z);
+    g.z = mk<float>(s.a2x, s.a2y, s.a2z);
     g.h0 = s.h0; g.h1 = s.h1; g.h2 = s.h2;
     g.brad = s.brad;
     return g;
-}
-
-__device__ __forceinline__ void slab_store(float *slab, int g, int lane, const Xf<float> &X) {
-    float *o = slab + (size_t)g * 7 * 32 + lane;
-    o[0] = X.r.x; o[32] = X.r.y; o[64] = X.r.z; o[96] = X.r.w;
-    o[128] = X.v.x; o[160] = X.v.y; o[192] = X.v.z;
-}
-__device__ __forceinline__ Xf<float> slab_load(const float *slab, int g, int lane) {
-    const float *o = slab + (size_t)g * 7 * 32 + lane;
-    Xf<float> X;
-    X.r.x = o[0]; X.r.y = o[32]; X.r.z = o[64]; X.r.w = o[96];
-    X.v.x = o[128]; X.v.y = o[160]; X.v.z = o[192];
-    return X;
 }
 
 struct UncList {
@@ -187,14 +175,18 @@ struct SinkEdgeFirst {
     }
 };
 
-/* ------------------------------------------------------------------ the kernel */
-template <class Src, class Sink>
-__global__ void __launch_bounds__(TMK_WARPS * 32, 2)
-k_states_warp(Image<float> im, WarpCfg cfg, Src src, Sink sink, UncList unc, unsigned long long *n_states) {
+/* ------------------------------------------------------------------ the kernel
+ * TILE threads = TILE states per CTA pass; phases are CTA-synchronous so that all warps of an SM
+ * execute the same (small) code region at a time - the instruction caches (L0 6 KB, L1.5 32 KB)
+ * are the scarce resource of this branchy code, not the FMA pipe. */
+template <class Src, class Sink, int TILE>
+__global__ void __launch_bounds__(TILE, 512 / TILE)
+k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, unsigned long long *n_states) {
     const size_t n = src.count();
     if (n == 0) return; /* dead bisection levels cost a launch, not a staging */
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
+    __shared__ uint32_t qn[4]; /* fill of q1 (quick), q2 (convex narrowphase), q3 (mesh narrowphase) */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DJoint<float> *J = im.joints;
@@ -239,113 +231,200 @@ k_states_warp(Image<float> im, WarpCfg cfg, Src src, Sink sink, UncList unc, uns
         PA = (const int *)(smem + cfg.off_pa);
     }
 
-    unsigned char *wbase = smem + cfg.off_warp + (size_t)warp * cfg.warp_bytes;
-    float *slab = (float *)wbase;                         /* [n_mg*7][32] geometry poses */
-    float *qs = (float *)(wbase + cfg.woff_q);            /* [n_sub][32] joint values */
-    uint32_t *queue = (uint32_t *)(wbase + cfg.woff_queue);
-    volatile uint8_t *flags = wbase + cfg.woff_flags;     /* [32] HIT flags, one per lane's state */
-    float *jslab = (float *)(wbase + cfg.woff_jslab);     /* poses of joints with non-consecutive children */
-    uint32_t *unc_x = (uint32_t *)(wbase + cfg.woff_unc);  /* [32] + [32]: undecided-item words of each lane's state */
-    uint32_t *unc_y = unc_x + 32;
+    float *slab = (float *)(smem + cfg.off_slab);       /* [n_mg*7][TILE] geometry poses */
+    float *qs = (float *)(smem + cfg.off_qs);           /* [n_sub][TILE] joint values */
+    float *jslab = (float *)(smem + cfg.off_jslab);     /* poses of joints with non-consecutive children */
+    uint32_t *q1 = (uint32_t *)(smem + cfg.off_q1);
+    uint32_t *q2 = (uint32_t *)(smem + cfg.off_q2);
+    uint32_t *q3 = (uint32_t *)(smem + cfg.off_q3);
+    volatile uint8_t *f_hit = smem + cfg.off_flags;     /* [TILE] */
+    uint32_t *unc_x = (uint32_t *)(smem + cfg.off_unc); /* [TILE] + [TILE]: undecided-item words of each state */
+    uint32_t *unc_y = unc_x + TILE;
 
-    const size_t n_groups = (n + 31) >> 5;
+    const size_t n_tiles = (n + TILE - 1) / TILE;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_joint = im.n_joint, n_sub = im.n_sub;
+    const float pad = Num<float>::eps() * 4.0f;
 
-    auto flush = [&](uint32_t qn, const typename Src::State &st) {
-        __syncwarp();
-        for (uint32_t i = lane; i < qn; i += 32) {
-            const uint32_t e = queue[i];
-            const int t = e >> 27, p = e & 0x7ffffff;
-            if (flags[t]) continue;
-            const uint32_t w = PAIRS[p];
-            const int a = w & 0xff, b = (w >> 8) & 0xffff;
-            const Xf<float> XA = slab_load(slab, a, t);
-            const DGeom<float> *B;
-            Xf<float> XB;
-            if ((w >> 24) & 1) {
-                B = &SG[b];
-                XB = xload(B->tf);
-            } else {
-                B = &MG[b];
-                XB = slab_load(slab, b, t);
-            }
-            const int r = test_geoms(MG[a], XA, *B, XB, im.meshes);
-            if (r == HIT) flags[t] = 1;
-            else if (r == UNC) {
-                /* the item belongs to lane t's state: fetch its identity from that lane's registers is
-                 * not possible here, so the owner lane's unc item words were parked in shared memory */
-                unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
-            }
-        }
-        __syncwarp();
-        (void)st;
+    auto pose_at = [&](int g, int t) {
+        const float *o = slab + (size_t)g * 7 * TILE + t;
+        Xf<float> X;
+        X.r.x = o[0]; X.r.y = o[TILE]; X.r.z = o[2 * TILE]; X.r.w = o[3 * TILE];
+        X.v.x = o[4 * TILE]; X.v.y = o[5 * TILE]; X.v.z = o[6 * TILE];
+        return X;
     };
 
-    for (size_t g = (size_t)blockIdx.x * TMK_WARPS + warp; g < n_groups; g += (size_t)gridDim.x * TMK_WARPS) {
-        const size_t s = g * 32 + lane;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t s = tile * TILE + tid;
         const typename Src::State st = src.prepare(s);
         const bool live = st.live && !im.static_hit;
-        bool hit = st.live && im.static_hit;
-        flags[lane] = live ? 0 : 1; /* dead lanes: nothing to evaluate, nothing queued */
+        if (tid < 4) qn[tid] = 0;
+        f_hit[tid] = (st.live && im.static_hit) ? 1 : 0;
         {
             const uint2 it = src.unc_item(st, 0u);
-            unc_x[lane] = it.x; unc_y[lane] = it.y;
+            unc_x[tid] = it.x; unc_y[tid] = it.y;
         }
         if (st.live)
-            for (int k = 0; k < n_sub; k++) qs[k * 32 + lane] = src.template load1<float>(st, k);
+            for (int k = 0; k < n_sub; k++) qs[k * TILE + tid] = src.template load1<float>(st, k);
         if (n_states) {
             const unsigned lm = __ballot_sync(0xffffffffu, live);
             if (lane == 0 && lm) atomicAdd(n_states, (unsigned long long)__popc(lm));
         }
-        __syncwarp();
-        uint32_t qn = 0;
-        Xf<float> cur;
-        cur.r.x = cur.r.y = cur.r.z = 0.f; cur.r.w = 1.f; cur.v = mk<float>(0.f, 0.f, 0.f);
-        for (int j = 0; j < n_joint; j++) {
-            const DJoint<float> &Jt = J[j];
-            const int par_id = Jt.parent;
-            Xf<float> par = cur;
-            if (par_id >= 0 && par_id != j - 1) par = slab_load(jslab, J[par_id].pad - 1, lane);
-            cur = fk_joint(xload(Jt.E), mk<float>(Jt.ax[0], Jt.ax[1], Jt.ax[2]), Jt.off, Jt.type, qs[Jt.qslot * 32 + lane],
-                           par_id >= 0 ? &par : (const Xf<float> *)nullptr);
-            if (Jt.pad > 0) slab_store(jslab, Jt.pad - 1, lane, cur);
-            for (int a = JG[j]; a < JG[j + 1]; a++) {
-                const DGeom<float> &A = MG[a];
-                const Xf<float> XA = xmul(cur, xload(A.tf));
-                slab_store(slab, a, lane, XA);
-                const QG qa = qg_from_pose(A, XA);
-                const int ka = A.shape;
-                const int p_end = PA[a + 1];
-                for (int p = PA[a]; p < p_end; p++) {
-                    const uint32_t w = PAIRS[p];
-                    const int b = (w >> 8) & 0xffff;
-                    bool need = false;
-                    if (live && !hit) {
-                        int r;
-                        if ((w >> 24) & 1) {
-                            r = quick_pair(ka, qa, SG[b].shape, qg_from_static(SQ[b]));
-                        } else {
-                            const DGeom<float> &B = MG[b];
-                            r = quick_pair(ka, qa, B.shape, qg_from_pose(B, slab_load(slab, b, lane)));
-                        }
-                        if (r == HIT) { hit = true; flags[lane] = 1; }
-                        else if (r == UNC) unc_emit(unc, src.unc_item(st, (uint32_t)p));
-                        else if (r == NEED) need = true;
+        __syncthreads();
+
+        /* ---- P1 + P2: joint chain in registers; every moving geometry meets its partner list at once ---- */
+        {
+            Xf<float> cur;
+            cur.r.x = cur.r.y = cur.r.z = 0.f; cur.r.w = 1.f; cur.v = mk<float>(0.f, 0.f, 0.f);
+            for (int j = 0; j < n_joint; j++) {
+                const DJoint<float> &Jt = J[j];
+                const int par_id = Jt.parent;
+                Xf<float> par = cur;
+                if (par_id >= 0 && par_id != j - 1) {
+                    const float *o = jslab + (size_t)(J[par_id].pad - 1) * 7 * TILE + tid;
+                    par.r.x = o[0]; par.r.y = o[TILE]; par.r.z = o[2 * TILE]; par.r.w = o[3 * TILE];
+                    par.v.x = o[4 * TILE]; par.v.y = o[5 * TILE]; par.v.z = o[6 * TILE];
+                }
+                cur = fk_joint(xload(Jt.E), mk<float>(Jt.ax[0], Jt.ax[1], Jt.ax[2]), Jt.off, Jt.type, qs[Jt.qslot * TILE + tid],
+                               par_id >= 0 ? &par : (const Xf<float> *)nullptr);
+                if (Jt.pad > 0) {
+                    float *o = jslab + (size_t)(Jt.pad - 1) * 7 * TILE + tid;
+                    o[0] = cur.r.x; o[TILE] = cur.r.y; o[2 * TILE] = cur.r.z; o[3 * TILE] = cur.r.w;
+                    o[4 * TILE] = cur.v.x; o[5 * TILE] = cur.v.y; o[6 * TILE] = cur.v.z;
+                }
+                for (int a = JG[j]; a < JG[j + 1]; a++) {
+                    const DGeom<float> &A = MG[a];
+                    const Xf<float> XA = xmul(cur, xload(A.tf));
+                    {
+                        float *o = slab + (size_t)a * 7 * TILE + tid;
+                        o[0] = XA.r.x; o[TILE] = XA.r.y; o[2 * TILE] = XA.r.z; o[3 * TILE] = XA.r.w;
+                        o[4 * TILE] = XA.v.x; o[5 * TILE] = XA.v.y; o[6 * TILE] = XA.v.z;
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, need);
-                    if (m) {
-                        if (qn + 32 > TMK_WQ) { flush(qn, st); qn = 0; }
-                        if (need) queue[qn + __popc(m & lt_mask)] = ((uint32_t)lane << 27) | (uint32_t)p;
-                        qn += __popc(m);
+                    const Vec3<float> ca = bound_centre(A, XA);
+                    const float ra = A.brad + pad;
+                    const int p_end = PA[a + 1];
+                    for (int p = PA[a]; p < p_end; p++) {
+                        const uint32_t w = PAIRS[p];
+                        const int b = (w >> 8) & 0xffff;
+                        bool pass = false;
+                        if (live) {
+                            if ((w >> 24) & 1) {
+                                const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
+                                const Vec3<float> d = mk<float>(c4.x - ca.x, c4.y - ca.y, c4.z - ca.z);
+                                if (((w >> 25) & 7) == K_BOX) {
+                                    /* bounding sphere of A against the box itself (exact point-box distance) */
+                                    const float4 x4 = *reinterpret_cast<const float4 *>(&SQ[b].a0x);
+                                    const float4 y4 = *reinterpret_cast<const float4 *>(&SQ[b].a1x);
+                                    const float4 z4 = *reinterpret_cast<const float4 *>(&SQ[b].a2x);
+                                    const float ex = fmaxf(fabsf(d.x * x4.x + d.y * x4.y + d.z * x4.z) - x4.w, 0.f);
+                                    const float ey = fmaxf(fabsf(d.x * y4.x + d.y * y4.y + d.z * y4.z) - y4.w, 0.f);
+                                    const float ez = fmaxf(fabsf(d.x * z4.x + d.y * z4.y + d.z * z4.z) - z4.w, 0.f);
+                                    pass = ex * ex + ey * ey + ez * ez <= ra * ra;
+                                } else {
+                                    const float reach = ra + c4.w;
+                                    pass = dot(d, d) <= reach * reach;
+                                }
+                            } else {
+                                const DGeom<float> &B = MG[b];
+                                const float *o = slab + (size_t)b * 7 * TILE + tid;
+                                Vec3<float> cb = mk<float>(o[4 * TILE], o[5 * TILE], o[6 * TILE]);
+                                if (B.shape == K_MESH) cb = bound_centre(B, pose_at(b, tid));
+                                const Vec3<float> d = cb - ca;
+                                const float reach = ra + B.brad;
+                                pass = dot(d, d) <= reach * reach;
+                            }
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, pass);
+                        if (m) {
+                            const int which = (w >> 28) == PC_MESH ? 2 : 0;
+                            uint32_t base = 0;
+                            if (lane == 0) base = atomicAdd(&qn[which], (uint32_t)__popc(m));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (pass) {
+                                const uint32_t idx = base + __popc(m & lt_mask);
+                                const uint32_t item = ((uint32_t)tid << 20) | (uint32_t)p;
+                                if (which == 0) {
+                                    if (idx < (uint32_t)cfg.q1_cap) q1[idx] = item;
+                                    else unc_emit(unc, src.unc_item(st, (uint32_t)p)); /* full: decide it exactly */
+                                } else {
+                                    if (idx < (uint32_t)cfg.q3_cap) q3[idx] = item;
+                                    else unc_emit(unc, src.unc_item(st, (uint32_t)p));
+                                }
+                            }
+                        }
                     }
                 }
             }
         }
-        flush(qn, st);
-        hit = hit || (live && flags[lane] != 0);
-        sink.emit(st, g, hit || !st.live, lane);
-        __syncwarp();
+        __syncthreads();
+
+        /* ---- Q: quick certificates, one thread per surviving (state, pair) ---- */
+        {
+            const uint32_t cnt = min(qn[0], (uint32_t)cfg.q1_cap);
+            for (uint32_t i = tid; i < cnt; i += TILE) {
+                const uint32_t e = q1[i];
+                const int t = e >> 20, p = e & 0xfffff;
+                if (f_hit[t]) continue;
+                const uint32_t w = PAIRS[p];
+                const int a = w & 0xff, b = (w >> 8) & 0xffff;
+                const DGeom<float> &A = MG[a];
+                const QG qa = qg_from_pose(A, pose_at(a, t));
+                int r;
+                if ((w >> 24) & 1) r = quick_pair(A.shape, qa, (int)((w >> 25) & 7), qg_from_static(SQ[b]));
+                else r = quick_pair(A.shape, qa, MG[b].shape, qg_from_pose(MG[b], pose_at(b, t)));
+                if (r == HIT) f_hit[t] = 1;
+                else if (r == UNC) unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+                else if (r == NEED) {
+                    const uint32_t idx = atomicAdd(&qn[1], 1u);
+                    if (idx < (uint32_t)cfg.q2_cap) q2[idx] = e;
+                    else unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- G: convex narrowphase (SAT / GJK) on what the certificates left open ---- */
+        {
+            const uint32_t cnt = min(qn[1], (uint32_t)cfg.q2_cap);
+            for (uint32_t i = tid; i < cnt; i += TILE) {
+                const uint32_t e = q2[i];
+                const int t = e >> 20, p = e & 0xfffff;
+                if (f_hit[t]) continue;
+                const uint32_t w = PAIRS[p];
+                const int a = w & 0xff, b = (w >> 8) & 0xffff;
+                const DGeom<float> *B;
+                Xf<float> XB;
+                if ((w >> 24) & 1) { B = &SG[b]; XB = xload(B->tf); }
+                else { B = &MG[b]; XB = pose_at(b, t); }
+                const int r = test_convex(shape_of(MG[a]), pose_at(a, t), shape_of(*B), XB);
+                if (r == HIT) f_hit[t] = 1;
+                else if (r == UNC) unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+            }
+        }
+        __syncthreads();
+
+        /* ---- M: mesh narrowphase (BVH traversal) ---- */
+        {
+            const uint32_t cnt = min(qn[2], (uint32_t)cfg.q3_cap);
+            for (uint32_t i = tid; i < cnt; i += TILE) {
+                const uint32_t e = q3[i];
+                const int t = e >> 20, p = e & 0xfffff;
+                if (f_hit[t]) continue;
+                const uint32_t w = PAIRS[p];
+                const int a = w & 0xff, b = (w >> 8) & 0xffff;
+                const DGeom<float> *B;
+                Xf<float> XB;
+                if ((w >> 24) & 1) { B = &SG[b]; XB = xload(B->tf); }
+                else { B = &MG[b]; XB = pose_at(b, t); }
+                const int r = test_geoms(MG[a], pose_at(a, t), *B, XB, im.meshes);
+                if (r == HIT) f_hit[t] = 1;
+                else if (r == UNC) unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+            }
+        }
+        __syncthreads();
+
+        sink.emit(st, tile * (TILE / 32) + warp, f_hit[tid] != 0 || !st.live, lane);
+        __syncthreads();
     }
 }
 
@@ -453,7 +532,11 @@ static inline int align16(int x) { return (x + 15) & ~15; }
 
 #define TMK_STAGE_BUDGET (40 * 1024) /* images up to this size are staged in shared memory */
 
-template <class Kernel> static void warp_configure(WarpCfg &cfg, const Image<float> &im, int n_jslab, Kernel kernel) {
+/* shared-memory plan for one (kernel, tile) choice; returns resident warps per SM (0 = does not fit) */
+template <class Kernel>
+static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel kernel, int tile, int sms, int optin,
+                     int sm_total) {
+    cfg.tile = tile;
     cfg.bytes_joint = align16(im.n_joint * (int)sizeof(DJoint<float>));
     cfg.bytes_mg = align16(im.n_mg * (int)sizeof(DGeom<float>));
     cfg.bytes_sg = align16(im.n_sg * (int)sizeof(DGeom<float>));
@@ -472,32 +555,60 @@ template <class Kernel> static void warp_configure(WarpCfg &cfg, const Image<flo
     cfg.off_jg = off; off += cfg.stage ? cfg.bytes_jg : 0;
     cfg.off_pa = off; off += cfg.stage ? cfg.bytes_pa : 0;
     off = (off + 127) & ~127;
-    cfg.off_warp = off;
-    int w = 0;
-    w += im.n_mg * 7 * 32 * 4;
-    cfg.woff_q = w; w += im.n_sub * 32 * 4;
-    cfg.woff_queue = w; w += TMK_WQ * 4;
-    cfg.woff_flags = w; w += 32;
-    cfg.woff_unc = w; w += 64 * 4;
-    cfg.woff_jslab = w; w += n_jslab * 7 * 32 * 4;
-    cfg.warp_bytes = (w + 127) & ~127;
-    cfg.smem = cfg.off_warp + TMK_WARPS * cfg.warp_bytes;
-    cfg.grid = 0;
-    int dev = 0, sms = 148, per_sm = 1, optin = 227 * 1024;
+    cfg.off_slab = off; off += im.n_mg * 7 * tile * 4;
+    cfg.off_qs = off; off += im.n_sub * tile * 4;
+    cfg.off_jslab = off; off += n_jslab * 7 * tile * 4;
+    cfg.off_flags = off; off += tile;
+    cfg.off_unc = off; off += 2 * tile * 4;
+    off = (off + 15) & ~15;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return 0;
+    int max_dyn = optin - (int)fa.sharedSizeBytes;
+    /* queues share what is left of the per-CTA budget at the best occupancy the fixed part allows */
+    const int per_cta_over = 1024 + (int)fa.sharedSizeBytes; /* driver reservation + static */
+    int best_ctas = 0, reg_ctas = 2048 / tile; /* at most 64 warps per SM; fewer if registers say so */
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, kernel, tile, 0) != cudaSuccess || reg_ctas < 1) return 0;
+    for (int ctas = reg_ctas; ctas >= 1; ctas--) {
+        int budget = sm_total / ctas - per_cta_over;
+        if (budget > max_dyn) budget = max_dyn;
+        int left = budget - off;
+        if (left >= 12 * 1024 || (ctas == 1 && left >= 4 * 1024)) { best_ctas = ctas; break; }
+    }
+    if (!best_ctas) return 0;
+    int budget = sm_total / best_ctas - per_cta_over;
+    if (budget > max_dyn) budget = max_dyn;
+    int left = (budget - off) & ~15;
+    /* 1/8 mesh queue, 1/8 narrowphase queue, the rest for the broadphase survivors */
+    cfg.q3_cap = left / 8 / 4;
+    cfg.q2_cap = left / 8 / 4;
+    cfg.q1_cap = (left - 4 * (cfg.q2_cap + cfg.q3_cap)) / 4;
+    if (cfg.q1_cap > (1 << 20)) cfg.q1_cap = 1 << 20;
+    cfg.off_q1 = off; off += cfg.q1_cap * 4;
+    cfg.off_q2 = off; off += cfg.q2_cap * 4;
+    cfg.off_q3 = off; off += cfg.q3_cap * 4;
+    cfg.smem = off;
+    /* the attribute is per function, not per collision context: always raise it to the maximum */
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess) return 0;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tile, cfg.smem);
+    if (per_sm < 1) return 0;
+    cfg.grid = sms * per_sm;
+    return per_sm * tile / 32;
+}
+
+template <class K256, class K128>
+static void tile_configure(TileCfg &cfg, const Image<float> &im, int n_jslab, K256 k256, K128 k128) {
+    int dev = 0, sms = 148, optin = 227 * 1024, sm_total = 228 * 1024;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cfg.smem = -1; return; }
-    int max_dyn = optin - (int)fa.sharedSizeBytes;
-    /* the attribute is per function, not per collision context: always raise it to the maximum */
-    if (cfg.smem > max_dyn || cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess) {
-        cfg.smem = -1;
-        return;
-    }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TMK_WARPS * 32, cfg.smem);
-    if (per_sm < 1) per_sm = 1;
-    cfg.grid = sms * per_sm;
+    cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    TileCfg c256, c128;
+    int w256 = tile_plan(c256, im, n_jslab, k256, 256, sms, optin, sm_total);
+    int w128 = tile_plan(c128, im, n_jslab, k128, 128, sms, optin, sm_total);
+    if (!w256 && !w128) { cfg.smem = -1; cfg.grid = 0; cfg.tile = 0; return; }
+    cfg = (w256 >= w128) ? c256 : c128;
 }
 
 } /* namespace tmk */
