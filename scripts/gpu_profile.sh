@@ -13,4 +13,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${TAG}_${WL}_launches.csv $CMD > gpurun_out/${TAG}_${WL}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 3 -c 2 \
     -f -o gpurun_out/${TAG}_${WL}_prof $CMD > gpurun_out/${TAG}_${WL}_ncu_full.log 2>&1
-tail -3 gpurun_out/${TAG}_${WL}_ncu_launches.log gpurun_out/${TAG}_${WL}_ncu_full.log
+tail -n 3 gpurun_out/${TAG}_${WL}_ncu_launches.log; tail -n 3 gpurun_out/${TAG}_${WL}_ncu_full.log

@@ -43,6 +43,18 @@ int h_quick_f32(int sa, const double *da, const double *ta, int sb, const double
     QG B = qg_make(sb, (float)db[0], (float)db[1], (float)db[2], brad(sb, db), xf_of<float>(tb), mk<float>(0.f, 0.f, 0.f));
     return quick_pair(sa, A, sb, B);
 }
+int h_convex_f32_iters(int sa, const double *da, const double *ta, int sb, const double *db, const double *tb, int *iters) {
+    *iters = 0;
+    return test_convex(shape_of<float>(sa, da), xf_of<float>(ta), shape_of<float>(sb, db), xf_of<float>(tb), iters);
+}
+int h_quick_tri_f32(int s, const double *d, const double *tri) {
+    return quick_tri(shape_of<float>(s, d), mk<float>((float)tri[0], (float)tri[1], (float)tri[2]),
+                     mk<float>((float)tri[3], (float)tri[4], (float)tri[5]), mk<float>((float)tri[6], (float)tri[7], (float)tri[8]));
+}
+int h_quick_tri_f64(int s, const double *d, const double *tri) {
+    return quick_tri(shape_of<double>(s, d), mk<double>(tri[0], tri[1], tri[2]), mk<double>(tri[3], tri[4], tri[5]),
+                     mk<double>(tri[6], tri[7], tri[8]));
+}
 int h_ompl_mid(int nd, int k) { return ompl_mid(nd, k); }
 /* FK chain in float vs double: returns the absolute pose of a serial revolute chain */
 void h_fk_chain(int n, const double *E, const double *axis, const double *q, int use_float, double *out) {

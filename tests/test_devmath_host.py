@@ -30,6 +30,8 @@ def H(built):
     for name in ("h_tri_shape_f32", "h_tri_shape_f64"):
         getattr(L, name).argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     L.h_quick_f32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    for name in ("h_quick_tri_f32", "h_quick_tri_f64"):
+        getattr(L, name).argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     L.h_tri_tri_f64.argtypes = [C.c_void_p, C.c_void_p]
     L.h_ompl_mid.argtypes = [C.c_int, C.c_int]
     L.h_fk_chain.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -175,6 +177,34 @@ def test_triangle_vs_shape(H, kind):
                 assert (r32 == HIT) == (st == O.HIT), (i, st, r32)
         n_unc += r32 == UNC
     assert n_unc < 0.05 * n
+
+
+@pytest.mark.parametrize("kind", [K_BOX, K_CYL])
+def test_quick_triangle_certificates_are_sound(H, kind):
+    """quick_tri (mesh leaves): SEP never on an oracle HIT, HIT never on an oracle FREE; in double
+    (eps = 0) its verdicts agree with the exact one."""
+    rng = np.random.default_rng(kind + 700)
+    n = 6000
+    n_dec = 0
+    ident = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    for i in range(n):
+        d, so, od, f = _rand_shape(rng, kind)
+        c = rng.uniform(-0.4, 0.4, 3)
+        tri = (c[None, :] + rng.uniform(-0.25, 0.25, (3, 3)) * rng.choice([0.05, 0.3, 1.0])).reshape(9)
+        if i % 5 == 0:
+            tri[[2, 5, 8]] = d[1 if kind == K_CYL else 2] + rng.choice([-1, 1]) * 10.0 ** rng.uniform(-7, -2)  # near a cap / face
+        st, ex = O.pair(so, od, f(ident), O.TRI, tri, None)
+        r32 = H.h_quick_tri_f32(kind, d.ctypes.data, tri.ctypes.data)
+        r64 = H.h_quick_tri_f64(kind, d.ctypes.data, tri.ctypes.data)
+        assert r32 in (SEP, HIT, NEED) and r64 in (SEP, HIT, NEED)
+        if r32 == SEP:
+            assert st != O.HIT, (i, "quick_tri SEP on an oracle HIT")
+        if r32 == HIT:
+            assert st != O.FREE, (i, "quick_tri HIT on an oracle FREE")
+        if st != O.BAND and r64 != NEED:
+            assert (r64 == HIT) == (st == O.HIT), (i, st, r64)
+        n_dec += r32 != NEED
+    assert n_dec > 0.5 * n, n_dec
 
 
 def test_triangle_triangle_exact(H):

@@ -18,7 +18,7 @@ import numpy as np
 from . import scenes as S
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtmkcl.so")
+LIB_PATH = os.environ.get("TMK_LIB") or os.path.join(HERE, "libtmkcl.so")  # TMK_LIB: A/B builds while tuning
 
 Q_ROWS_F64, Q_ROWS_F32, Q_SOA_F32 = 0, 1, 2
 

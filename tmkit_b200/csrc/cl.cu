@@ -171,7 +171,7 @@ static void mesh_compile(const struct aa_rx_mesh *m, HostMesh &hm) {
 
 /* ------------------------------------------------------------------ the collision context */
 struct ImageDev {
-    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa;
+    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4;
     Image<float> f;
     Image<double> d;
     std::vector<uint32_t> h_pairs;
@@ -320,7 +320,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
                     &cl->d_gout, &cl->d_tf, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
-                    &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa};
+                    &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4};
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     cudaFreeHost(cl->h_cnt);
@@ -508,7 +508,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     /* candidate pairs: every (moving, other) pair that is not same-frame / allowed.  A pair of two
      * moving geometries is owned by the later one (its partner's pose already exists when the
      * kernel reaches it).  Grouped by owner, then by narrowphase class. */
-    struct P { uint32_t w; int fa, fb, owner; };
+    struct P { uint32_t w; int fa, fb, owner, seg; };
     std::vector<P> pairs;
     for (size_t a = 0; a < cl->n_g; a++) {
         if (g2m[a] < 0) continue;
@@ -522,16 +522,18 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
             p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls, cl->geoms[b].shape)
                               : pair_pack(g2m[a], g2s[b], 1, cls, cl->geoms[b].shape);
             p.fa = fa; p.fb = fb; p.owner = g2m[a];
+            p.seg = g2m[b] >= 0 ? 2 : ((cl->geoms[b].shape == TMK_BOX || cl->geoms[b].shape == TMK_MESH) ? 1 : 0);
             pairs.push_back(p);
         }
     }
     std::stable_sort(pairs.begin(), pairs.end(), [](const P &x, const P &y) {
         if (x.owner != y.owner) return x.owner < y.owner;
+        if (x.seg != y.seg) return x.seg < y.seg;
         return (x.w >> 28) < (y.w >> 28);
     });
-    std::vector<int> pa_begin(mg.size() + 1, 0);
-    for (auto &p : pairs) pa_begin[p.owner + 1]++;
-    for (size_t a = 0; a < mg.size(); a++) pa_begin[a + 1] += pa_begin[a];
+    std::vector<int> pa_begin(3 * mg.size() + 1, 0);
+    for (auto &p : pairs) pa_begin[3 * p.owner + p.seg + 1]++;
+    for (size_t k = 0; k < 3 * mg.size(); k++) pa_begin[k + 1] += pa_begin[k];
     im.h_pairs.clear(); im.pair_fa.clear(); im.pair_fb.clear();
     for (auto &p : pairs) { im.h_pairs.push_back(p.w); im.pair_fa.push_back(p.fa); im.pair_fb.push_back(p.fb); }
     if (im.h_pairs.size() >= (1u << 27)) tmk_die("batch: too many candidate pairs");
@@ -554,6 +556,12 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         Q.cx = (float)c[0]; Q.cy = (float)c[1]; Q.cz = (float)c[2];
         Q.brad = (float)(G.brad * (1 + 1e-6));
         Q.h0 = (float)G.dim[0]; Q.h1 = (float)G.dim[1]; Q.h2 = (float)G.dim[2];
+        if (G.shape == TMK_MESH) { /* broadphase sees a static mesh as the oriented box of its root node */
+            const BvhNode &root = cl->hmesh[G.mesh].nodes[0];
+            Q.h0 = 0.5f * (root.hi[0] - root.lo[0]) * (1 + 1e-6f) + 1e-6f;
+            Q.h1 = 0.5f * (root.hi[1] - root.lo[1]) * (1 + 1e-6f) + 1e-6f;
+            Q.h2 = 0.5f * (root.hi[2] - root.lo[2]) * (1 + 1e-6f) + 1e-6f;
+        }
     }
 
     /* hoisted static-static pairs, evaluated once (double) */
@@ -584,6 +592,17 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     upload(im.sq, sq, cl->stream);
     upload(im.jg, jg_begin, cl->stream);
     upload(im.pa, pa_begin, cl->stream);
+    {
+        std::vector<float4> ps4(pairs.size() + 1);
+        for (size_t k = 0; k < pairs.size(); k++) {
+            uint32_t w = pairs[k].w;
+            if ((w >> 24) & 1) {
+                const SQuick &Q = sq[(w >> 8) & 0xffff];
+                ps4[k] = make_float4(Q.cx, Q.cy, Q.cz, Q.brad);
+            } else ps4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        upload(im.ps4, ps4, cl->stream);
+    }
     CK(cudaStreamSynchronize(cl->stream));
 
     im.d.joints = (const DJoint<double> *)im.jd.p; im.f.joints = (const DJoint<float> *)im.jf.p;
@@ -600,6 +619,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     im.d.sq = im.f.sq = im.sq.p;
     im.d.jg_begin = im.f.jg_begin = (const int *)im.jg.p;
     im.d.pa_begin = im.f.pa_begin = (const int *)im.pa.p;
+    im.d.ps4 = im.f.ps4 = im.ps4.p;
     tile_configure(im.wcfg, im.f, n_jslab, k_states_tile<SrcConfigs, SinkBits, 256>, k_states_tile<SrcConfigs, SinkBits, 128>);
     tile_configure(im.wcfg_e, im.f, n_jslab, k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256>,
                    k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128>);

@@ -487,9 +487,9 @@ TMK_HD int test_tri_vs_shape(const Shape<T> &S, Vec3<T> p0, Vec3<T> p1, Vec3<T> 
 }
 
 template <typename T>
-TMK_HD int test_convex(const Shape<T> &A, const Xf<T> &XA, const Shape<T> &B, const Xf<T> &XB) {
+TMK_HD int test_convex(const Shape<T> &A, const Xf<T> &XA, const Shape<T> &B, const Xf<T> &XB, int *iters = nullptr) {
     /* order so that kind(A) <= kind(B) */
-    if (A.kind > B.kind) return test_convex(B, XB, A, XA);
+    if (A.kind > B.kind) return test_convex(B, XB, A, XA, iters);
     if (A.kind == K_SPHERE) {
         if (B.kind == K_SPHERE) {
             Vec3<T> d = XA.v - XB.v;
@@ -508,7 +508,7 @@ TMK_HD int test_convex(const Shape<T> &A, const Xf<T> &XA, const Shape<T> &B, co
     G.R = R;
     G.t = rel.v;
     G.p0 = G.p1 = G.p2 = mk<T>(0, 0, 0);
-    return gjk_pair<T>(A.kind, A.a, A.b, (A.kind == K_BOX) ? A.c : T(0), G);
+    return gjk_pair<T>(A.kind, A.a, A.b, (A.kind == K_BOX) ? A.c : T(0), G, iters);
 }
 
 /* ------------------------------------------------------------------ quick certificates (FP32 broadphase stage)
@@ -646,6 +646,57 @@ template <typename T> struct MeshRef {
     T cx, cy, cz;         /* bounding-sphere centre, mesh-local */
 };
 
+/* quick verdict of a triangle (points in S's local frame) against a box / cylinder: SEP by one of
+ * the shape's own axes, the triangle's plane normal or (cylinder) the radial direction towards the
+ * triangle; HIT when a vertex lies inside the shape by more than the allowance; else NEED. */
+template <typename T> TMK_HD int quick_tri(const Shape<T> &S, Vec3<T> p0, Vec3<T> p1, Vec3<T> p2) {
+    const T eps = Num<T>::eps();
+    const T zlo = t_min(p0.z, t_min(p1.z, p2.z)), zhi = t_max(p0.z, t_max(p1.z, p2.z));
+    Vec3<T> n = cross(p1 - p0, p2 - p0);
+    const T n2 = dot(n, n);
+    if (S.kind == K_BOX) {
+        if (zlo > S.c + eps || zhi < -S.c - eps) return SEP;
+        if (t_min(p0.x, t_min(p1.x, p2.x)) > S.a + eps || t_max(p0.x, t_max(p1.x, p2.x)) < -S.a - eps) return SEP;
+        if (t_min(p0.y, t_min(p1.y, p2.y)) > S.b + eps || t_max(p0.y, t_max(p1.y, p2.y)) < -S.b - eps) return SEP;
+        if (n2 > Num<T>::tiny()) {
+            const T inv = T(1) / t_sqrt(n2);
+            const T d = t_abs(dot(n, p0)) * inv;
+            const T proj = (S.a * t_abs(n.x) + S.b * t_abs(n.y) + S.c * t_abs(n.z)) * inv;
+            if (d > proj + eps) return SEP;
+        }
+        const T hx = S.a - eps, hy = S.b - eps, hz = S.c - eps;
+        if (t_abs(p0.x) < hx && t_abs(p0.y) < hy && t_abs(p0.z) < hz) return HIT;
+        if (t_abs(p1.x) < hx && t_abs(p1.y) < hy && t_abs(p1.z) < hz) return HIT;
+        if (t_abs(p2.x) < hx && t_abs(p2.y) < hy && t_abs(p2.z) < hz) return HIT;
+        return NEED;
+    }
+    /* cylinder: S.a = radius, S.b = half height, axis z */
+    if (zlo > S.b + eps || zhi < -S.b - eps) return SEP;
+    if (n2 > Num<T>::tiny()) {
+        const T inv = T(1) / t_sqrt(n2);
+        const T d = t_abs(dot(n, p0)) * inv;
+        const T proj = (S.b * t_abs(n.z) + S.a * t_sqrt(n.x * n.x + n.y * n.y)) * inv;
+        if (d > proj + eps) return SEP;
+    }
+    {
+        const T cx = p0.x + p1.x + p2.x, cy = p0.y + p1.y + p2.y;
+        const T c2 = cx * cx + cy * cy;
+        if (c2 > Num<T>::tiny()) {
+            const T inv = T(1) / t_sqrt(c2);
+            const T mx = cx * inv, my = cy * inv;
+            const T lo = t_min(p0.x * mx + p0.y * my, t_min(p1.x * mx + p1.y * my, p2.x * mx + p2.y * my));
+            if (lo > S.a + eps) return SEP;
+        }
+    }
+    const T r2 = (S.a - eps) * (S.a - eps), hz = S.b - eps;
+    if (S.a > eps) {
+        if (t_abs(p0.z) < hz && p0.x * p0.x + p0.y * p0.y < r2) return HIT;
+        if (t_abs(p1.z) < hz && p1.x * p1.x + p1.y * p1.y < r2) return HIT;
+        if (t_abs(p2.z) < hz && p2.x * p2.x + p2.y * p2.y < r2) return HIT;
+    }
+    return NEED;
+}
+
 /* shape S (sphere/box/cyl, pose XS) against mesh (pose XM) */
 template <typename T>
 TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> &S, const Xf<T> &XS, T s_brad,
@@ -654,14 +705,33 @@ TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> 
     Xf<T> m_in_s = xrel(XS, XM); /* mesh in S frame */
     Mat3<T> Rms = q2m(m_in_s.r);
     Vec3<T> c = s_in_m.v;
-    T rad = s_brad + Num<T>::eps() * T(4);
+    const T pad = Num<T>::eps() * T(4);
+    T rad = s_brad + pad;
     T rad2 = rad * rad;
+    /* extents of S along the mesh axes (rows of Rms = S's axes in the mesh frame, transposed) */
+    T ex, ey, ez;
+    if (S.kind == K_SPHERE) {
+        ex = ey = ez = S.a + pad;
+    } else if (S.kind == K_BOX) {
+        ex = S.a * t_abs(Rms.m00) + S.b * t_abs(Rms.m10) + S.c * t_abs(Rms.m20) + pad;
+        ey = S.a * t_abs(Rms.m01) + S.b * t_abs(Rms.m11) + S.c * t_abs(Rms.m21) + pad;
+        ez = S.a * t_abs(Rms.m02) + S.b * t_abs(Rms.m12) + S.c * t_abs(Rms.m22) + pad;
+    } else { /* cylinder axis in the mesh frame = third row of Rms */
+        const T ux = Rms.m20, uy = Rms.m21, uz = Rms.m22;
+        ex = S.b * t_abs(ux) + S.a * t_sqrt(t_max(T(0), T(1) - ux * ux)) + pad + T(1e-6) * S.a;
+        ey = S.b * t_abs(uy) + S.a * t_sqrt(t_max(T(0), T(1) - uy * uy)) + pad + T(1e-6) * S.a;
+        ez = S.b * t_abs(uz) + S.a * t_sqrt(t_max(T(0), T(1) - uz * uz)) + pad + T(1e-6) * S.a;
+    }
     int stack[32];
     int sp = 0;
     stack[sp++] = 0;
     int result = SEP;
     while (sp > 0) {
         BvhNode nd = M.nodes[stack[--sp]];
+        /* S's axis-aligned bounds in the mesh frame against the node, then its bounding sphere */
+        if (c.x - ex > T(nd.hi[0]) || c.x + ex < T(nd.lo[0]) || c.y - ey > T(nd.hi[1]) || c.y + ey < T(nd.lo[1]) ||
+            c.z - ez > T(nd.hi[2]) || c.z + ez < T(nd.lo[2]))
+            continue;
         T dx = t_max(t_max(T(nd.lo[0]) - c.x, c.x - T(nd.hi[0])), T(0));
         T dy = t_max(t_max(T(nd.lo[1]) - c.y, c.y - T(nd.hi[1])), T(0));
         T dz = t_max(t_max(T(nd.lo[2]) - c.z, c.z - T(nd.hi[2])), T(0));
@@ -673,7 +743,12 @@ TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> 
                 Vec3<T> p1 = mv(Rms, mk<T>(tp[3], tp[4], tp[5])) + m_in_s.v;
                 Vec3<T> p2 = mv(Rms, mk<T>(tp[6], tp[7], tp[8])) + m_in_s.v;
                 if (n_leaf) (*n_leaf)++;
-                int r = test_tri_vs_shape(S, p0, p1, p2);
+                int r;
+                if (S.kind == K_SPHERE) r = test_tri_vs_shape(S, p0, p1, p2);
+                else {
+                    r = quick_tri(S, p0, p1, p2);
+                    if (r == NEED) r = test_tri_vs_shape(S, p0, p1, p2);
+                }
                 if (r == HIT) return HIT;
                 if (r == UNC) result = UNC;
             }

@@ -53,7 +53,9 @@ template <typename T> struct Image {
     const MeshRef<T> *meshes;
     const void *sq;      /* SQuick[n_sg]: world-frame quick tables of the static geometry (float image) */
     const int *jg_begin; /* [n_joint+1]: moving geometries of joint j are mg[jg_begin[j] .. jg_begin[j+1]) */
-    const int *pa_begin; /* [n_mg+1]: pairs owned by moving geometry a are pairs[pa_begin[a] .. pa_begin[a+1]) */
+    const int *pa_begin; /* [3*n_mg+1]: pairs owned by moving geometry a, in three segments - static partners
+                          * tested by bounding sphere [3a], static boxes [3a+1], moving partners [3a+2] .. [3a+3] */
+    const void *ps4;     /* float4[n_pair]: bounding centre + radius of the static partner, in pair order */
     int n_joint, n_mg, n_sg, n_pair;
     int n_sub;
     int static_hit; /* a non-allowed static-static pair collides: every configuration is invalid */

@@ -38,8 +38,8 @@ struct SQuick {
 
 struct TileCfg {
     int stage; /* 1: image staged in shared memory */
-    int off_joint, off_mg, off_sg, off_pairs, off_sq, off_jg, off_pa;
-    int bytes_joint, bytes_mg, bytes_sg, bytes_pairs, bytes_sq, bytes_jg, bytes_pa;
+    int off_joint, off_mg, off_sg, off_pairs, off_sq, off_jg, off_pa, off_ps4;
+    int bytes_joint, bytes_mg, bytes_sg, bytes_pairs, bytes_sq, bytes_jg, bytes_pa, bytes_ps4;
     int off_slab, off_qs, off_jslab, off_q1, off_q2, off_q3, off_flags, off_unc;
     int q1_cap, q2_cap, q3_cap;
     int tile; /* threads per CTA = states per pass: 256 or 128 */
@@ -186,7 +186,9 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     if (n == 0) return; /* dead bisection levels cost a launch, not a staging */
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    __shared__ uint32_t qn[4]; /* fill of q1 (quick), q2 (convex narrowphase), q3 (mesh narrowphase) */
+    __shared__ uint32_t qn[4];          /* [1]: fill of q2 (convex narrowphase) */
+    __shared__ uint32_t wn1[TILE / 32]; /* fill of each warp's private region of q1 (quick) ... */
+    __shared__ uint32_t wn3[TILE / 32]; /* ... and of q3 (mesh narrowphase) */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DJoint<float> *J = im.joints;
@@ -195,6 +197,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     const uint32_t *PAIRS = im.pairs;
     const SQuick *SQ = (const SQuick *)im.sq;
     const int *JG = im.jg_begin, *PA = im.pa_begin;
+    const float4 *PS4 = (const float4 *)im.ps4;
 
     if (cfg.stage) {
         if (tid == 0) {
@@ -204,7 +207,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         __syncthreads();
         if (tid == 0) {
             uint32_t total = (uint32_t)(cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_sg + cfg.bytes_pairs + cfg.bytes_sq +
-                                        cfg.bytes_jg + cfg.bytes_pa);
+                                        cfg.bytes_jg + cfg.bytes_pa + cfg.bytes_ps4);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(total)
                          : "memory");
             bulk_g2s(smem + cfg.off_joint, im.joints, (uint32_t)cfg.bytes_joint, &bar);
@@ -214,6 +217,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             if (cfg.bytes_sq) bulk_g2s(smem + cfg.off_sq, im.sq, (uint32_t)cfg.bytes_sq, &bar);
             bulk_g2s(smem + cfg.off_jg, im.jg_begin, (uint32_t)cfg.bytes_jg, &bar);
             bulk_g2s(smem + cfg.off_pa, im.pa_begin, (uint32_t)cfg.bytes_pa, &bar);
+            if (cfg.bytes_ps4) bulk_g2s(smem + cfg.off_ps4, im.ps4, (uint32_t)cfg.bytes_ps4, &bar);
         }
         uint32_t done = 0;
         while (!done) {
@@ -229,6 +233,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         SQ = (const SQuick *)(smem + cfg.off_sq);
         JG = (const int *)(smem + cfg.off_jg);
         PA = (const int *)(smem + cfg.off_pa);
+        PS4 = (const float4 *)(smem + cfg.off_ps4);
     }
 
     float *slab = (float *)(smem + cfg.off_slab);       /* [n_mg*7][TILE] geometry poses */
@@ -274,6 +279,8 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
 
         /* ---- P1 + P2: joint chain in registers; every moving geometry meets its partner list at once ---- */
         {
+            uint32_t n1 = 0, n3 = 0; /* warp-uniform */
+            uint32_t *q1w = q1 + (size_t)warp * cfg.q1_cap, *q3w = q3 + (size_t)warp * cfg.q3_cap;
             Xf<float> cur;
             cur.r.x = cur.r.y = cur.r.z = 0.f; cur.r.w = 1.f; cur.v = mk<float>(0.f, 0.f, 0.f);
             for (int j = 0; j < n_joint; j++) {
@@ -302,67 +309,75 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                     }
                     const Vec3<float> ca = bound_centre(A, XA);
                     const float ra = A.brad + pad;
-                    const int p_end = PA[a + 1];
-                    for (int p = PA[a]; p < p_end; p++) {
-                        const uint32_t w = PAIRS[p];
-                        const int b = (w >> 8) & 0xffff;
-                        bool pass = false;
-                        if (live) {
-                            if ((w >> 24) & 1) {
-                                const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
-                                const Vec3<float> d = mk<float>(c4.x - ca.x, c4.y - ca.y, c4.z - ca.z);
-                                if (((w >> 25) & 7) == K_BOX) {
-                                    /* bounding sphere of A against the box itself (exact point-box distance) */
-                                    const float4 x4 = *reinterpret_cast<const float4 *>(&SQ[b].a0x);
-                                    const float4 y4 = *reinterpret_cast<const float4 *>(&SQ[b].a1x);
-                                    const float4 z4 = *reinterpret_cast<const float4 *>(&SQ[b].a2x);
-                                    const float ex = fmaxf(fabsf(d.x * x4.x + d.y * x4.y + d.z * x4.z) - x4.w, 0.f);
-                                    const float ey = fmaxf(fabsf(d.x * y4.x + d.y * y4.y + d.z * y4.z) - y4.w, 0.f);
-                                    const float ez = fmaxf(fabsf(d.x * z4.x + d.y * z4.y + d.z * z4.z) - z4.w, 0.f);
-                                    pass = ex * ex + ey * ey + ez * ez <= ra * ra;
-                                } else {
-                                    const float reach = ra + c4.w;
-                                    pass = dot(d, d) <= reach * reach;
-                                }
-                            } else {
-                                const DGeom<float> &B = MG[b];
-                                const float *o = slab + (size_t)b * 7 * TILE + tid;
-                                Vec3<float> cb = mk<float>(o[4 * TILE], o[5 * TILE], o[6 * TILE]);
-                                if (B.shape == K_MESH) cb = bound_centre(B, pose_at(b, tid));
-                                const Vec3<float> d = cb - ca;
-                                const float reach = ra + B.brad;
-                                pass = dot(d, d) <= reach * reach;
-                            }
-                        }
+                    /* survivors of the warp-uniform tests go to the warp's own region of q1 (convex pairs)
+                     * or q3 (mesh pairs): the fill counts are warp-uniform registers, no atomics */
+                    auto enqueue = [&](int p, bool pass) {
                         const unsigned m = __ballot_sync(0xffffffffu, pass);
                         if (m) {
-                            const int which = (w >> 28) == PC_MESH ? 2 : 0;
-                            uint32_t base = 0;
-                            if (lane == 0) base = atomicAdd(&qn[which], (uint32_t)__popc(m));
-                            base = __shfl_sync(0xffffffffu, base, 0);
+                            const bool mesh = (PAIRS[p] >> 28) == PC_MESH;
+                            const uint32_t idx = (mesh ? n3 : n1) + __popc(m & lt_mask);
                             if (pass) {
-                                const uint32_t idx = base + __popc(m & lt_mask);
                                 const uint32_t item = ((uint32_t)tid << 20) | (uint32_t)p;
-                                if (which == 0) {
-                                    if (idx < (uint32_t)cfg.q1_cap) q1[idx] = item;
-                                    else unc_emit(unc, src.unc_item(st, (uint32_t)p)); /* full: decide it exactly */
-                                } else {
-                                    if (idx < (uint32_t)cfg.q3_cap) q3[idx] = item;
-                                    else unc_emit(unc, src.unc_item(st, (uint32_t)p));
-                                }
+                                if (!mesh && idx < (uint32_t)cfg.q1_cap) q1w[idx] = item;
+                                else if (mesh && idx < (uint32_t)cfg.q3_cap) q3w[idx] = item;
+                                else unc_emit(unc, src.unc_item(st, (uint32_t)p)); /* region full: decide it exactly */
                             }
+                            if (mesh) n3 += __popc(m); else n1 += __popc(m);
                         }
+                    };
+                    int p = PA[3 * a];
+                    const int e0 = PA[3 * a + 1], e1 = PA[3 * a + 2], e2 = PA[3 * a + 3];
+                    /* static partners by bounding sphere */
+                    for (; p < e0; p++) {
+                        const float4 c4 = PS4[p];
+                        const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+                        const float reach = ra + c4.w;
+                        enqueue(p, live && dx * dx + dy * dy + dz * dz <= reach * reach);
+                    }
+                    /* static boxes: bounding sphere of A against the box itself (exact point-box distance) */
+                    for (; p < e1; p++) {
+                        const int b = (PAIRS[p] >> 8) & 0xffff;
+                        const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
+                        const float4 x4 = *reinterpret_cast<const float4 *>(&SQ[b].a0x);
+                        const float4 y4 = *reinterpret_cast<const float4 *>(&SQ[b].a1x);
+                        const float4 z4 = *reinterpret_cast<const float4 *>(&SQ[b].a2x);
+                        const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+                        const float ex = fmaxf(fabsf(dx * x4.x + dy * x4.y + dz * x4.z) - x4.w, 0.f);
+                        const float ey = fmaxf(fabsf(dx * y4.x + dy * y4.y + dz * y4.z) - y4.w, 0.f);
+                        const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
+                        enqueue(p, live && ex * ex + ey * ey + ez * ez <= ra * ra);
+                    }
+                    /* moving partners (their poses are already in the slab) */
+                    for (; p < e2; p++) {
+                        const int b = (PAIRS[p] >> 8) & 0xffff;
+                        const DGeom<float> &B = MG[b];
+                        const float *o = slab + (size_t)b * 7 * TILE + tid;
+                        Vec3<float> cb = mk<float>(o[4 * TILE], o[5 * TILE], o[6 * TILE]);
+                        if (B.shape == K_MESH) cb = bound_centre(B, pose_at(b, tid));
+                        const Vec3<float> d = cb - ca;
+                        const float reach = ra + B.brad;
+                        enqueue(p, live && dot(d, d) <= reach * reach);
                     }
                 }
+            }
+            if (lane == 0) {
+                wn1[warp] = min(n1, (uint32_t)cfg.q1_cap);
+                wn3[warp] = min(n3, (uint32_t)cfg.q3_cap);
             }
         }
         __syncthreads();
 
         /* ---- Q: quick certificates, one thread per surviving (state, pair) ---- */
         {
-            const uint32_t cnt = min(qn[0], (uint32_t)cfg.q1_cap);
-            for (uint32_t i = tid; i < cnt; i += TILE) {
-                const uint32_t e = q1[i];
+            uint32_t total = 0;
+#pragma unroll
+            for (int k = 0; k < TILE / 32; k++) total += wn1[k];
+            for (uint32_t i = tid; i < total; i += TILE) {
+                /* dense index -> (warp region, offset) */
+                uint32_t off = i;
+                int k = 0;
+                while (off >= wn1[k]) { off -= wn1[k]; k++; }
+                const uint32_t e = q1[(size_t)k * cfg.q1_cap + off];
                 const int t = e >> 20, p = e & 0xfffff;
                 if (f_hit[t]) continue;
                 const uint32_t w = PAIRS[p];
@@ -405,9 +420,14 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
 
         /* ---- M: mesh narrowphase (BVH traversal) ---- */
         {
-            const uint32_t cnt = min(qn[2], (uint32_t)cfg.q3_cap);
-            for (uint32_t i = tid; i < cnt; i += TILE) {
-                const uint32_t e = q3[i];
+            uint32_t total = 0;
+#pragma unroll
+            for (int k = 0; k < TILE / 32; k++) total += wn3[k];
+            for (uint32_t i = tid; i < total; i += TILE) {
+                uint32_t off = i;
+                int k = 0;
+                while (off >= wn3[k]) { off -= wn3[k]; k++; }
+                const uint32_t e = q3[(size_t)k * cfg.q3_cap + off];
                 const int t = e >> 20, p = e & 0xfffff;
                 if (f_hit[t]) continue;
                 const uint32_t w = PAIRS[p];
@@ -543,8 +563,10 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
     cfg.bytes_pairs = align16(im.n_pair * 4);
     cfg.bytes_sq = align16(im.n_sg * (int)sizeof(SQuick));
     cfg.bytes_jg = align16((im.n_joint + 1) * 4);
-    cfg.bytes_pa = align16((im.n_mg + 1) * 4);
-    int image = cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_sg + cfg.bytes_pairs + cfg.bytes_sq + cfg.bytes_jg + cfg.bytes_pa;
+    cfg.bytes_pa = align16((3 * im.n_mg + 1) * 4);
+    cfg.bytes_ps4 = im.n_pair * 16;
+    int image = cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_sg + cfg.bytes_pairs + cfg.bytes_sq + cfg.bytes_jg + cfg.bytes_pa +
+                cfg.bytes_ps4;
     cfg.stage = image <= TMK_STAGE_BUDGET ? 1 : 0;
     int off = 0;
     cfg.off_joint = off; off += cfg.stage ? cfg.bytes_joint : 0;
@@ -554,6 +576,7 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
     cfg.off_sq = off; off += cfg.stage ? cfg.bytes_sq : 0;
     cfg.off_jg = off; off += cfg.stage ? cfg.bytes_jg : 0;
     cfg.off_pa = off; off += cfg.stage ? cfg.bytes_pa : 0;
+    cfg.off_ps4 = off; off += cfg.stage ? cfg.bytes_ps4 : 0;
     off = (off + 127) & ~127;
     cfg.off_slab = off; off += im.n_mg * 7 * tile * 4;
     cfg.off_qs = off; off += im.n_sub * tile * 4;
@@ -579,14 +602,16 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
     int budget = sm_total / best_ctas - per_cta_over;
     if (budget > max_dyn) budget = max_dyn;
     int left = (budget - off) & ~15;
-    /* 1/8 mesh queue, 1/8 narrowphase queue, the rest for the broadphase survivors */
-    cfg.q3_cap = left / 8 / 4;
+    /* q1 / q3 are split into one private region per warp (capacities below are PER WARP);
+     * 9/16 broadphase survivors, 2/16 convex narrowphase, 5/16 mesh narrowphase */
+    const int nw = tile / 32;
     cfg.q2_cap = left / 8 / 4;
-    cfg.q1_cap = (left - 4 * (cfg.q2_cap + cfg.q3_cap)) / 4;
-    if (cfg.q1_cap > (1 << 20)) cfg.q1_cap = 1 << 20;
-    cfg.off_q1 = off; off += cfg.q1_cap * 4;
+    cfg.q3_cap = (left * 5 / 16) / 4 / nw;
+    cfg.q1_cap = (left - 4 * cfg.q2_cap - 4 * cfg.q3_cap * nw) / 4 / nw;
+    if (cfg.q1_cap > (1 << 16)) cfg.q1_cap = 1 << 16;
+    cfg.off_q1 = off; off += cfg.q1_cap * nw * 4;
     cfg.off_q2 = off; off += cfg.q2_cap * 4;
-    cfg.off_q3 = off; off += cfg.q3_cap * 4;
+    cfg.off_q3 = off; off += cfg.q3_cap * nw * 4;
     cfg.smem = off;
     /* the attribute is per function, not per collision context: always raise it to the maximum */
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess) return 0;
@@ -608,6 +633,9 @@ static void tile_configure(TileCfg &cfg, const Image<float> &im, int n_jslab, K2
     int w256 = tile_plan(c256, im, n_jslab, k256, 256, sms, optin, sm_total);
     int w128 = tile_plan(c128, im, n_jslab, k128, 128, sms, optin, sm_total);
     if (!w256 && !w128) { cfg.smem = -1; cfg.grid = 0; cfg.tile = 0; return; }
+    const char *force = getenv("TMK_TILE"); /* tuning aid */
+    if (force && atoi(force) == 128 && w128) { cfg = c128; return; }
+    if (force && atoi(force) == 256 && w256) { cfg = c256; return; }
     cfg = (w256 >= w128) ? c256 : c128;
 }
 
