@@ -189,6 +189,8 @@ struct aa_rx_cl {
     uint32_t *allowed; /* own copy */
     uint64_t allow_serial;
     cudaStream_t stream;
+    cudaStream_t copy_stream; /* host-buffer entry points: H2D of chunk k+1 overlaps the kernels of chunk k */
+    cudaEvent_t ev_copy[8];
 
     /* frame-relative geometry + meshes */
     std::vector<DGeom<double>> geoms;
@@ -208,7 +210,9 @@ struct aa_rx_cl {
     int track, stats_on;
     std::vector<uint8_t> last_pairhit;
     struct tmk_batch_stats stats;
-    int use_tile; /* 1: warp-pipeline kernel (default), 0: thread-per-configuration kernel */
+    int use_tile; /* 1: tile-pipeline kernel (default), 0: thread-per-configuration kernel */
+    UncList cur_unc;      /* undecided list of the batch in flight */
+    cudaEvent_t *cur_ev;  /* its timing events (NULL when timing is off) */
 
     /* device-time instrumentation: events around the main kernel / the re-check kernel of every launch */
     int timing;
@@ -309,6 +313,8 @@ extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
     cl->use_tile = getenv("TMK_NO_TILE") ? 0 : 1;
     memset(&cl->stats, 0, sizeof(cl->stats));
     CK(cudaStreamCreateWithFlags(&cl->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&cl->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&cl->ev_copy[k], cudaEventDisableTiming));
     CK(cudaMallocHost((void **)&cl->h_cnt, 64));
     build_geoms(cl);
     return cl;
@@ -324,6 +330,8 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     cudaFreeHost(cl->h_cnt);
+    for (int k = 0; k < 8; k++) cudaEventDestroy(cl->ev_copy[k]);
+    cudaStreamDestroy(cl->copy_stream);
     cudaStreamDestroy(cl->stream);
     free(cl->allowed);
     delete cl;
@@ -639,17 +647,19 @@ static void stats_begin(struct aa_rx_cl *cl) {
 static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     UncList u;
     u.cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states / 2), 0x7fffffffu);
-    cl->d_unc.need(sizeof(uint2) * (size_t)u.cap);
+    cl->d_unc.need(sizeof(uint4) * (size_t)u.cap);
     cl->d_cnt.need(128);
     CK(cudaMemsetAsync(cl->d_cnt.p, 0, 128, s));
-    u.items = (uint2 *)cl->d_unc.p;
+    u.items = (uint4 *)cl->d_unc.p;
     u.n = (uint32_t *)cl->d_cnt.p;
     u.overflow = (uint32_t *)cl->d_cnt.p + 1;
     return u;
 }
 
+/* dQ / d_bits address the whole batch of n_cfg configurations; [chunk_begin, chunk_end) is the part this
+ * call evaluates (chunk_end == 0: all of it).  Chunks must be issued in order on the same stream. */
 static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, int layout, size_t ld,
-                           uint32_t *d_bits, cudaStream_t s) {
+                           uint32_t *d_bits, cudaStream_t s, size_t chunk_begin = 0, size_t chunk_end = 0) {
     ImageDev &im = cl->img;
     if (n_cfg > 0xfffffff0u) tmk_die("batch: more than 2^32 configurations in one call");
     uint8_t *pairhit = nullptr;
@@ -660,16 +670,20 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
     }
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
     if (cl->use_tile && im.wcfg.smem > 0 && !pairhit && !st) {
-        /* fast path: FP32 warp pipelines, then the exact re-check of the undecided pairs */
-        UncList u = unc_list(cl, n_cfg, s);
+        /* fast path: FP32 tile pipeline, then the exact re-check of the undecided pairs.  chunk_* let the
+         * host-buffer entry point run the pipeline chunk by chunk behind the copies (one undecided list
+         * and one re-check for the whole batch) */
+        if (chunk_begin == 0) cl->cur_unc = unc_list(cl, n_cfg, s);
+        UncList u = cl->cur_unc;
         if (n_cfg == 0) return;
+        const size_t c_end = chunk_end ? chunk_end : n_cfg;
         SrcConfigs src;
-        src.p = dQ; src.layout = layout; src.ld = ld; src.n = n_cfg;
+        src.p = dQ; src.layout = layout; src.ld = ld; src.n = c_end - chunk_begin; src.s_begin = chunk_begin;
         SinkBits sink;
         sink.bits = d_bits;
         const int T = im.wcfg.tile;
-        unsigned grid = (unsigned)std::min<size_t>((n_cfg + T - 1) / T, (size_t)im.wcfg.grid);
-        cudaEvent_t *ev = timing_begin(cl, s);
+        unsigned grid = (unsigned)std::min<size_t>((src.n + T - 1) / T, (size_t)im.wcfg.grid);
+        cudaEvent_t *ev = chunk_begin == 0 ? (cl->cur_ev = timing_begin(cl, s)) : cl->cur_ev;
         if (T == 256)
             k_states_tile<SrcConfigs, SinkBits, 256><<<grid, 256, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
                                                                                       (unsigned long long *)nullptr);
@@ -677,15 +691,19 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
             k_states_tile<SrcConfigs, SinkBits, 128><<<grid, 128, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
                                                                                       (unsigned long long *)nullptr);
         CK(cudaGetLastError());
+        cl->stats.n_launches += 1;
+        if (c_end < n_cfg) return;
         if (ev) CK(cudaEventRecord(ev[1], s));
+        src.n = n_cfg; src.s_begin = 0;
         k_recheck_items<SrcConfigs, SinkBits><<<148, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         k_overflow_all<SrcConfigs, SinkBits><<<148 * 2, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         if (ev) CK(cudaEventRecord(ev[2], s));
-        cl->stats.n_launches += 3;
+        cl->stats.n_launches += 2;
         return;
     }
+    if (chunk_begin != 0 || (chunk_end && chunk_end < n_cfg)) tmk_die("internal: chunked launch on the instrumented path");
     /* instrumented path (statistics / collision tracking): one thread per configuration */
     QSrc qs;
     qs.p = dQ; qs.p1 = nullptr; qs.layout = layout; qs.ld = ld;
@@ -713,7 +731,7 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
     if (!(seg_len > 0)) tmk_die("edges: seg_len must be positive");
     if (n_edge > 0x7ffffff0u) tmk_die("edges: more than 2^31 edges in one call");
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
-    if (cl->use_tile && im.wcfg_e.smem > 0 && !st && im.h_pairs.size() < (1u << 19)) {
+    if (cl->use_tile && im.wcfg_e.smem > 0 && !st ) {
         /* fast path: bisection levels through the warp pipelines (warp.cuh) */
         UncList u = unc_list(cl, n_edge * 4, s);
         if (n_edge == 0) return;
@@ -833,8 +851,26 @@ static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, 
     size_t nw = (n_cfg + 31) / 32;
     cl->d_q.need(n_cfg * ldQ * esz + 16);
     cl->d_bits.need(sizeof(uint32_t) * (nw + 1));
-    if (n_cfg) CK(cudaMemcpyAsync(cl->d_q.p, Q, n_cfg * ldQ * esz, cudaMemcpyHostToDevice, cl->stream));
-    launch_configs(cl, n_cfg, cl->d_q.p, layout, ldQ, (uint32_t *)cl->d_bits.p, cl->stream);
+    /* chunk = two full waves of the persistent grid (no tail effect inside a chunk) */
+    const size_t wave = (size_t)std::max(1, cl->img.wcfg.grid) * (size_t)std::max(32, cl->img.wcfg.tile);
+    const size_t CH = 2 * wave;
+    if (n_cfg <= CH + CH / 2 || cl->stats_on || cl->track || !cl->use_tile || cl->img.wcfg.smem <= 0) {
+        if (n_cfg) CK(cudaMemcpyAsync(cl->d_q.p, Q, n_cfg * ldQ * esz, cudaMemcpyHostToDevice, cl->stream));
+        launch_configs(cl, n_cfg, cl->d_q.p, layout, ldQ, (uint32_t *)cl->d_bits.p, cl->stream);
+    } else {
+        /* software pipeline: the copy of chunk k+1 (copy stream) overlaps the kernel of chunk k */
+        size_t k = 0;
+        for (size_t off = 0; off < n_cfg; k++) {
+            size_t end = off + CH;
+            if (end + CH / 2 > n_cfg) end = n_cfg; /* fold a short tail into the last chunk */
+            CK(cudaMemcpyAsync((char *)cl->d_q.p + off * ldQ * esz, (const char *)Q + off * ldQ * esz, (end - off) * ldQ * esz,
+                               cudaMemcpyHostToDevice, cl->copy_stream));
+            CK(cudaEventRecord(cl->ev_copy[k & 7], cl->copy_stream));
+            CK(cudaStreamWaitEvent(cl->stream, cl->ev_copy[k & 7], 0));
+            launch_configs(cl, n_cfg, cl->d_q.p, layout, ldQ, (uint32_t *)cl->d_bits.p, cl->stream, off, end);
+            off = end;
+        }
+    }
     if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
     stats_end(cl, n_cfg, cl->stream);
     size_t bad = count_invalid(valid_bits, n_cfg);

@@ -697,10 +697,29 @@ template <typename T> TMK_HD int quick_tri(const Shape<T> &S, Vec3<T> p0, Vec3<T
     return NEED;
 }
 
-/* shape S (sphere/box/cyl, pose XS) against mesh (pose XM) */
+/* what to do with a triangle the FP32 certificates cannot decide: by default the whole pair becomes
+ * UNC; the batch kernels pass a functor that records the single triangle for the exact re-check */
+struct NoTri {
+    static constexpr bool enabled = false;
+    TMK_HD void operator()(int) const {}
+};
+
+/* one triangle of a mesh (pose XM) against shape S (pose XS) */
 template <typename T>
+TMK_HD int test_mesh_tri_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> &S, const Xf<T> &XS, int tri) {
+    Xf<T> m_in_s = xrel(XS, XM);
+    Mat3<T> Rms = q2m(m_in_s.r);
+    const T *tp = M.tris + 9 * (size_t)tri;
+    Vec3<T> p0 = mv(Rms, mk<T>(tp[0], tp[1], tp[2])) + m_in_s.v;
+    Vec3<T> p1 = mv(Rms, mk<T>(tp[3], tp[4], tp[5])) + m_in_s.v;
+    Vec3<T> p2 = mv(Rms, mk<T>(tp[6], tp[7], tp[8])) + m_in_s.v;
+    return test_tri_vs_shape(S, p0, p1, p2);
+}
+
+/* shape S (sphere/box/cyl, pose XS) against mesh (pose XM) */
+template <typename T, class UncTri = NoTri>
 TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> &S, const Xf<T> &XS, T s_brad,
-                           unsigned *n_leaf = nullptr) {
+                           unsigned *n_leaf = nullptr, UncTri on_unc_tri = UncTri()) {
     Xf<T> s_in_m = xrel(XM, XS); /* S in mesh frame */
     Xf<T> m_in_s = xrel(XS, XM); /* mesh in S frame */
     Mat3<T> Rms = q2m(m_in_s.r);
@@ -750,7 +769,10 @@ TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> 
                     if (r == NEED) r = test_tri_vs_shape(S, p0, p1, p2);
                 }
                 if (r == HIT) return HIT;
-                if (r == UNC) result = UNC;
+                if (r == UNC) {
+                    if (UncTri::enabled) on_unc_tri(nd.a + k);
+                    else result = UNC;
+                }
             }
         } else {
             if (sp + 2 <= 32) {

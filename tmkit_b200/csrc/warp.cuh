@@ -27,7 +27,6 @@
 
 namespace tmk {
 
-
 /* world-frame quick geometry: centre, axes (columns of the rotation), dims, bounding radius */
 struct SQuick {
     float cx, cy, cz, brad;
@@ -70,41 +69,51 @@ __device__ __forceinline__ QG qg_from_static(const SQuick &s) {
 }
 
 struct UncList {
-    uint2 *items;       /* (state, pair) */
+    uint4 *items;       /* x,y = state identity (Src::unc_id), z = pair, w = mesh triangle or TMK_WHOLE_PAIR */
     uint32_t *n;        /* appended count (may exceed cap) */
     uint32_t cap;
     uint32_t *overflow; /* set when an item was dropped: the brute-force double kernel then runs */
 };
-__device__ __forceinline__ void unc_emit(const UncList &u, uint2 item) {
+#define TMK_WHOLE_PAIR 0xffffffffu
+__device__ __forceinline__ void unc_emit(const UncList &u, uint32_t id_x, uint32_t id_y, uint32_t pair, uint32_t tri) {
     uint32_t i = atomicAdd(u.n, 1u);
-    if (i < u.cap) u.items[i] = item;
+    if (i < u.cap) u.items[i] = make_uint4(id_x, id_y, pair, tri);
     else *u.overflow = 1u;
 }
+/* mesh narrowphase hands its undecided TRIANGLES over one by one (the exact re-check of a whole
+ * mesh pair in one thread is a long serial chain; single triangles are not) */
+struct TriEmit {
+    static constexpr bool enabled = true;
+    UncList u;
+    uint32_t id_x, id_y, pair;
+    __device__ __forceinline__ void operator()(int tri) const { unc_emit(u, id_x, id_y, pair, (uint32_t)tri); }
+};
 
 /* ------------------------------------------------------------------ sources of states, sinks of verdicts
  * Src:  count(), prepare(s) -> State (with .live), load1<T>(State, k) = k-th joint value,
- *       unc_item(State, pair) / from_unc(item, &pair) to carry a state through the undecided list.
+ *       unc_id(State) / from_id(x, y) to carry a state's identity through the undecided list.
  * Sink: emit(State, g, hit, lane) called convergently by the 32 lanes of group g; mark_hit(State). */
 struct SrcConfigs {
     const void *p;
     int layout;
     size_t ld, n;
+    size_t s_begin; /* this launch covers states s_begin .. s_begin + n - 1 of the batch at p */
     struct State { size_t s; bool live; };
     __device__ __forceinline__ size_t count() const { return n; }
-    __device__ __forceinline__ State prepare(size_t s) const { State st; st.s = s; st.live = s < n; return st; }
+    __device__ __forceinline__ State prepare(size_t s) const { State st; st.s = s_begin + s; st.live = s < n; return st; }
     template <typename T> __device__ __forceinline__ T load1(const State &st, int k) const {
         return load_q<T>(p, layout, ld, st.s, k);
     }
-    __device__ __forceinline__ uint2 unc_item(const State &st, uint32_t pair) const { return make_uint2((uint32_t)st.s, pair); }
-    __device__ __forceinline__ State from_unc(uint2 it, uint32_t *pair) const { *pair = it.y; return prepare(it.x); }
+    __device__ __forceinline__ uint2 unc_id(const State &st) const { return make_uint2((uint32_t)st.s, 0u); }
+    __device__ __forceinline__ State from_id(uint32_t x, uint32_t y) const { (void)y; State st; st.s = x; st.live = true; return st; }
 };
 
 struct SinkBits {
     uint32_t *bits;
     __device__ __forceinline__ void emit(const SrcConfigs::State &st, size_t g, bool hit, int lane) const {
-        (void)st;
+        (void)g;
         const unsigned valid = __ballot_sync(0xffffffffu, !hit);
-        if (lane == 0) bits[g] = valid;
+        if (lane == 0) bits[st.s >> 5] = valid;
     }
     __device__ __forceinline__ void mark_hit(const SrcConfigs::State &st) const {
         atomicAnd(&bits[st.s >> 5], ~(1u << (st.s & 31)));
@@ -154,14 +163,8 @@ struct SrcEdgeLevel {
         const double a = load_q<double>(p0, layout, ld, st.e, k);
         return (T)__dadd_rn(a, __dmul_rn(__dsub_rn(b, a), st.t));
     }
-    /* undecided item: x = edge, y = position << 19 | pair */
-    __device__ __forceinline__ uint2 unc_item(const State &st, uint32_t pair) const {
-        return make_uint2(st.e, ((uint32_t)st.pos << 19) | pair);
-    }
-    __device__ __forceinline__ State from_unc(uint2 it, uint32_t *pair) const {
-        *pair = it.y & 0x7ffffu;
-        return at(it.x, (int)(it.y >> 19));
-    }
+    __device__ __forceinline__ uint2 unc_id(const State &st) const { return make_uint2(st.e, (uint32_t)st.pos); }
+    __device__ __forceinline__ State from_id(uint32_t x, uint32_t y) const { return at(x, (int)y); }
 };
 
 struct SinkEdgeFirst {
@@ -266,7 +269,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         if (tid < 4) qn[tid] = 0;
         f_hit[tid] = (st.live && im.static_hit) ? 1 : 0;
         {
-            const uint2 it = src.unc_item(st, 0u);
+            const uint2 it = src.unc_id(st);
             unc_x[tid] = it.x; unc_y[tid] = it.y;
         }
         if (st.live)
@@ -320,7 +323,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                                 const uint32_t item = ((uint32_t)tid << 20) | (uint32_t)p;
                                 if (!mesh && idx < (uint32_t)cfg.q1_cap) q1w[idx] = item;
                                 else if (mesh && idx < (uint32_t)cfg.q3_cap) q3w[idx] = item;
-                                else unc_emit(unc, src.unc_item(st, (uint32_t)p)); /* region full: decide it exactly */
+                                else unc_emit(unc, unc_x[tid], unc_y[tid], (uint32_t)p, TMK_WHOLE_PAIR); /* region full: decide it exactly */
                             }
                             if (mesh) n3 += __popc(m); else n1 += __popc(m);
                         }
@@ -388,11 +391,11 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                 if ((w >> 24) & 1) r = quick_pair(A.shape, qa, (int)((w >> 25) & 7), qg_from_static(SQ[b]));
                 else r = quick_pair(A.shape, qa, MG[b].shape, qg_from_pose(MG[b], pose_at(b, t)));
                 if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
                 else if (r == NEED) {
                     const uint32_t idx = atomicAdd(&qn[1], 1u);
                     if (idx < (uint32_t)cfg.q2_cap) q2[idx] = e;
-                    else unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+                    else unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
                 }
             }
         }
@@ -413,7 +416,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                 else { B = &MG[b]; XB = pose_at(b, t); }
                 const int r = test_convex(shape_of(MG[a]), pose_at(a, t), shape_of(*B), XB);
                 if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
             }
         }
         __syncthreads();
@@ -436,9 +439,11 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                 Xf<float> XB;
                 if ((w >> 24) & 1) { B = &SG[b]; XB = xload(B->tf); }
                 else { B = &MG[b]; XB = pose_at(b, t); }
-                const int r = test_geoms(MG[a], pose_at(a, t), *B, XB, im.meshes);
+                TriEmit on_tri;
+                on_tri.u = unc; on_tri.id_x = unc_x[t]; on_tri.id_y = unc_y[t]; on_tri.pair = (uint32_t)p;
+                const int r = test_geoms(MG[a], pose_at(a, t), *B, XB, im.meshes, on_tri);
                 if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, make_uint2(unc_x[t], unc_y[t] | (uint32_t)p));
+                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
             }
         }
         __syncthreads();
@@ -454,8 +459,9 @@ __global__ void __launch_bounds__(128) k_recheck_items(Image<double> im, Src src
     uint32_t n = *unc.n;
     if (n > unc.cap) n = unc.cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t pair;
-        const typename Src::State st = src.from_unc(unc.items[i], &pair);
+        const uint4 it = unc.items[i];
+        const uint32_t pair = it.z;
+        const typename Src::State st = src.from_id(it.x, it.y);
         if (!st.live) continue;
         double q[TMK_MAXSUB];
         for (int k = 0; k < im.n_sub; k++) q[k] = src.template load1<double>(st, k);
@@ -466,7 +472,11 @@ __global__ void __launch_bounds__(128) k_recheck_items(Image<double> im, Src src
         const DGeom<double> &A = im.mg[a];
         const DGeom<double> &B = (w >> 24) & 1 ? im.sg[b] : im.mg[b];
         const Xf<double> XB = (w >> 24) & 1 ? xload(B.tf) : gp[b];
-        if (test_geoms(A, gp[a], B, XB, im.meshes) == HIT) sink.mark_hit(st);
+        int r;
+        if (it.w == TMK_WHOLE_PAIR) r = test_geoms(A, gp[a], B, XB, im.meshes);
+        else if (A.shape == K_MESH) r = test_mesh_tri_shape(im.meshes[A.mesh], gp[a], shape_of(B), XB, (int)it.w);
+        else r = test_mesh_tri_shape(im.meshes[B.mesh], XB, shape_of(A), gp[a], (int)it.w);
+        if (r == HIT) sink.mark_hit(st);
     }
 }
 
