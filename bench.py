@@ -364,6 +364,14 @@ def main():
         return
 
     hbm_peak, peak_kind, sm_max = load_peaks()
+    traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f).get(args.workload)
+        if tj:
+            traffic = tj["bytes_per_launch"] * (n_units / tj["units_per_launch"])
+    except Exception:
+        traffic = None
     bytes_unit = (4 * len(sub) * (2 if edges else 1)) + 1.0 / 8
     achieved_gbs = bytes_unit * n_units / (k_ms * 1e-3) / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
@@ -385,13 +393,14 @@ def main():
         # the path is bound by the FP32 (FMA) pipe, not HBM and not the tensor cores (SURVEY.md 8d,
         # DESIGN.md): `roofline` is the FP32 one, `roofline_hbm` the contract's HBM form beside it
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_probe, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp32_probe, "traffic": None, "kernel": kernel, "kernel_ms": k_ms,
+                     "frac": achieved_tf / fp32_probe, "traffic": traffic, "kernel": kernel, "kernel_ms": k_ms,
                      "recheck_kernel_ms": rk_ms, "flops_per_unit": flops_unit, "flops_per_state": f_cfg,
                      "states_per_unit": states_per_unit,
                      "peak_kind": "measured on this device by tmk_fp32_peak_tflops (FFMA loop)",
                      "peak_nominal": fp32_nominal},
         "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind, "kernel": kernel,
+                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "algorithmic_bytes": bytes_unit * n_units,
+                         "peak_kind": peak_kind, "kernel": kernel,
                          "kernel_ms": k_ms, "bytes_per_unit": bytes_unit},
         "counters": {"joints": int(st.n_joints), "moving_geoms": int(st.n_moving_geoms), "pairs": int(st.n_pairs),
                      "narrow_per_state": [st.n_narrow[k] / max(1, st.n_states) for k in range(4)],
