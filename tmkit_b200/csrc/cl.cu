@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
-#include "warp.cuh"
+#include "pipeline.cuh"
 #include "tmk_internal.h"
 
 using namespace tmk;
@@ -732,7 +732,7 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
     if (n_edge > 0x7ffffff0u) tmk_die("edges: more than 2^31 edges in one call");
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
     if (cl->use_tile && im.wcfg_e.smem > 0 && !st ) {
-        /* fast path: bisection levels through the warp pipelines (warp.cuh) */
+        /* fast path: bisection levels through the warp pipelines (pipeline.cuh) */
         UncList u = unc_list(cl, n_edge * 4, s);
         if (n_edge == 0) return;
         const uint32_t ne = (uint32_t)n_edge;

@@ -1,23 +1,24 @@
-/* warp.cuh - the batched validity kernel, second generation: warp-autonomous pipelines.
+/* pipeline.cuh - the batched state-validity pipeline (K1 + K2 + K3 fused; K4 on top of it).
  *
- * One CTA = 8 warps; every warp owns groups of 32 states (one state per lane) and runs the whole
- * pipeline for them with no CTA-wide barrier after the scene image has been staged:
+ * Persistent CTAs of TILE threads walk tiles of TILE states; the phases are CTA-synchronous so that
+ * the warps of an SM execute the same small code region at a time (instruction-cache capacity, not
+ * the FMA pipe, is what this branchy code runs out of - see profiles/README.md):
  *
- *   stage   scene tables (joints, geometry, grouped pair list, quick tables) copied once per CTA into
- *           shared memory with TMA 1-D bulk copies completing on an mbarrier (images too large
- *           for the staging budget are read through L1 instead)
- *   P1+P2   one lane = one state.  The joint chain runs in registers; as soon as the pose of a
- *           moving geometry exists it is written to the warp's pose slab ([geom*7+k][lane], bank
- *           conflict free) and its partner list is walked.  The list is warp-uniform, so the
- *           bounding-sphere test and the QUICK CERTIFICATES (closed forms for spheres, face /
- *           axis separating-axis tests and centre-containment tests for boxes and cylinders) run
- *           without divergence.  Pairs they cannot decide are compacted with ballot/popc into the
- *           warp's queue.
- *   P3      one lane = one queued (state, pair): SAT / GJK / BVH narrowphase from dev_math.cuh on
- *           the poses in the slab.
- *   out     a state is valid unless a HIT was certified.  Pairs the FP32 certificates cannot decide
- *           (UNC) are appended to a global (state, pair) list; k_recheck_items re-evaluates exactly
- *           those pairs in double precision and clears the state's result on a HIT.
+ *   stage   scene tables (joints, geometry, grouped pair list, per-pair bounding spheres, quick tables)
+ *           copied once per CTA into shared memory with TMA 1-D bulk copies completing on an
+ *           mbarrier (images above the staging budget are read through L1 instead)
+ *   P1+P2   one thread = one state.  The joint chain runs in registers; as soon as the pose of a
+ *           moving geometry exists it is written to the pose slab ([geom*7+k][thread], bank conflict
+ *           free) and meets its partner list: static partners by bounding sphere, static boxes and
+ *           meshes by the exact sphere-to-oriented-box distance, moving partners from the slab.  The
+ *           list is warp-uniform; survivors are compacted with ballot/popc into the warp's private
+ *           region of the queue (fill counts are warp-uniform registers, no atomics).
+ *   Q       one thread = one surviving (state, pair): quick certificates (dev_math.cuh quick_pair).
+ *   G       exact convex narrowphase (SAT / GJK) on what the certificates left open.
+ *   M       mesh narrowphase: AABB-tree traversal, per-triangle certificates, GJK on the rest.
+ *   out     a state is valid unless a HIT was certified.  Pairs or single mesh triangles the FP32
+ *           certificates cannot decide (UNC) are appended to a global list; k_recheck_items
+ *           re-evaluates exactly those in double precision and clears the state's result on a HIT.
  *
  * Src supplies the states (configurations, or interior states of swept edges); Sink consumes the
  * verdicts (validity bitmap, or per-edge first-invalid positions).
