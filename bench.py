@@ -106,19 +106,37 @@ def flops_per_config(st, n_joint_rev):
     return 61.0 * st.n_joints + 34.0 * n_joint_rev + 33.0 * st.n_moving_geoms + 11.0 * st.n_pairs + narrow
 
 
-def make_problem():
+# workload -> (scene builder, varied joints, units per step per GPU, kind, BASELINE.json config, description)
+def workload_table():
+    from tmkit_b200 import scenes as S
+    return {
+        "configs": (lambda: S.baxter_sussman(), S.RIGHT_ARM, N_CFG, "configs",
+                    "BASELINE configs[1]: 2^20 random Baxter 7-DOF right-arm configurations vs the Sussman block scene "
+                    "(restated Baxter fixture), per GPU"),
+        "edges": (lambda: S.baxter_sussman(), S.RIGHT_ARM, N_EDGE, "edges",
+                  "BASELINE configs[2]: 100K random RRT-like Baxter right-arm segments, OMPL 1% resolution, per GPU"),
+        "blocks": (lambda: S.blocksworld_scene(32, seed=32), S.RIGHT_ARM, N_CFG, "configs",
+                   "BASELINE configs[3]: 2^20 right-arm configurations, 32-block tabletop, one block in the gripper, "
+                   "mesh robot vs box obstacles, per GPU"),
+        "clutter": (lambda: S.clutter_scene(512, seed=0), S.RIGHT_ARM + S.LEFT_ARM, 1 << 21, "configs",
+                    "BASELINE configs[4]: 2^21 dual-arm (14-DOF) configurations vs 512 random primitives, per GPU "
+                    "(16M over 8 GPUs)"),
+    }
+
+
+def make_problem(workload="configs"):
     from tmkit_b200 import amino as A
     from tmkit_b200 import scenes as S
     from tmkit_b200 import workloads as W
-    sc = S.baxter_sussman()
-    return sc, S, W, A
+    build, names, n_units, kind, desc = workload_table()[workload]
+    return build(), S, W, A, names, n_units, kind, desc
 
 
 def cpu_baseline(workload: str, seconds_budget: float = 12.0):
     """The CPU restatement (oracle, early-out mode = aa_rx_cl_check with a NULL set) on all host
     cores, on a bounded sample of the same workload."""
     from oracle import oracle as O
-    sc, S, W, _ = make_problem()
+    sc, S, W, _, names, n_units_w, kind, _ = make_problem(workload)
     so = "/tmp/libtmkoracle_native.so"
     try:
         path = O.build(force=True, march_native=True, out=so)
@@ -128,10 +146,10 @@ def cpu_baseline(workload: str, seconds_budget: float = 12.0):
     orc = O.OracleScene(flat, libpath=path)
     q0 = np.asarray([S.Q0.get(n, 0.0) for n in orc.config_names])
     orc.allow_config(q0)
-    sub = orc.config_ids(S.RIGHT_ARM)
-    lim = W.arm_limit_table(S.RIGHT_ARM)
+    sub = orc.config_ids(names)
+    lim = W.arm_limit_table(names)
     cores = os.cpu_count() or 1
-    if workload == "edges":
+    if kind == "edges":
         n = 2000
         a, b = W.random_edges(lim, n, seed=0)
         t0 = time.perf_counter()
@@ -143,7 +161,7 @@ def cpu_baseline(workload: str, seconds_budget: float = 12.0):
         orc.check_edges(sub, q0, a, b, W.seg_len(lim), early_out=True, threads=cores)
         dt = time.perf_counter() - t0
         return n2 / dt, cores, f"{n2} of {N_EDGE} RRT-like edges, early-out, all cores", n2, dt
-    n = 20000
+    n = 4000
     Q = W.random_configs(lim, n, seed=0)
     t0 = time.perf_counter()
     orc.check_batch(sub, q0, Q, early_out=True, threads=cores)
@@ -153,7 +171,7 @@ def cpu_baseline(workload: str, seconds_budget: float = 12.0):
     t0 = time.perf_counter()
     orc.check_batch(sub, q0, Q, early_out=True, threads=cores)
     dt = time.perf_counter() - t0
-    return n2 / dt, cores, f"{n2} of {N_CFG} configurations, early-out, all cores", n2, dt
+    return n2 / dt, cores, f"{n2} of {n_units_w} configurations, early-out, all cores", n2, dt
 
 
 def run_reference(args):
@@ -181,17 +199,16 @@ def run_reference(args):
 
 
 def metric_name(workload):
-    return ("collision-checked configs/sec (FK + collision, Baxter right arm vs Sussman scene)" if workload == "configs"
-            else "swept-edge checks/sec (RRT-Connect segments at OMPL resolution)")
+    return {"configs": "collision-checked configs/sec (FK + collision, Baxter right arm vs Sussman scene)",
+            "edges": "swept-edge checks/sec (RRT-Connect segments at OMPL resolution)",
+            "blocks": "collision-checked configs/sec (FK + collision, Baxter right arm, 32-block tabletop)",
+            "clutter": "collision-checked configs/sec (FK + collision, dual-arm Baxter vs 512 primitives)"}[workload]
 
 
 def config_dict(workload):
-    if workload == "configs":
-        return {"workload": "BASELINE configs[1]: 2^20 random Baxter 7-DOF right-arm configurations vs the Sussman "
-                            "block scene (restated Baxter fixture), per GPU",
-                "units_per_step_per_gpu": N_CFG, "l2": f"inputs rotate over a ring of {RING} batches (> L2)"}
-    return {"workload": "BASELINE configs[2]: 100K random RRT-like Baxter right-arm segments, OMPL 1% resolution, per GPU",
-            "units_per_step_per_gpu": N_EDGE, "l2": f"inputs rotate over a ring of {RING} batches"}
+    _, _, n_units, kind, desc = workload_table()[workload]
+    return {"workload": desc, "units_per_step_per_gpu": n_units,
+            "l2": f"inputs rotate over a ring of {RING} distinct batches" + (" (> L2)" if kind == "configs" else "")}
 
 
 def main():
@@ -200,7 +217,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="configs", choices=["configs", "edges"])
+    ap.add_argument("--workload", default="configs", choices=["configs", "edges", "blocks", "clutter"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -223,16 +240,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    sc, S, W, A = make_problem()
+    sc, S, W, A, names, n_units, kind, _ = make_problem(args.workload)
     sg = A.SceneGraph.from_scene(sc)
     q0 = np.asarray([S.Q0.get(n, 0.0) for n in sg.config_names()])
     sg.allow_config(q0)  # the reference allows what collides at the start configuration
     cl = A.Collision(sg)
-    sub = sg.config_indices(S.RIGHT_ARM)
-    lim = W.arm_limit_table(S.RIGHT_ARM)
+    sub = sg.config_indices(names)
+    lim = W.arm_limit_table(names)
     seg = W.seg_len(lim)
-    edges = args.workload == "edges"
-    n_units = N_EDGE if edges else N_CFG
+    edges = kind == "edges"
     unit = "edges/s" if edges else "configs/s"
     nw = (n_units + 31) // 32
 

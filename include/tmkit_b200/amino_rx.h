@@ -208,6 +208,72 @@ struct tmk_batch_stats {
 void aa_rx_cl_batch_stats(struct aa_rx_cl *cl, struct tmk_batch_stats *out);
 void aa_rx_cl_stats_enable(struct aa_rx_cl *cl, int enable); /* instrumented (slower) runs */
 
+/* ---------------------------------------------------------------------------------------
+ * "Next" rows: the caller of the path.  Host C on top of the batched entry points
+ * above; the shapes follow what robray:motion-plan drives in Amino (lisp/python/tmsmtpy.lisp:55-60:
+ * sub-scene-graph, start configuration, workspace goal, :simplify t, :track-collisions t, :timeout).
+ * ------------------------------------------------------------------------------------- */
+int aa_rx_sg_frame_type(const struct aa_rx_sg *sg, aa_rx_frame_id id);   /* 0 fixed, 1 revolute, 2 prismatic */
+aa_rx_config_id aa_rx_sg_frame_config(const struct aa_rx_sg *sg, aa_rx_frame_id id); /* AA_RX_CONFIG_NONE if fixed */
+void aa_rx_sg_frame_axis(const struct aa_rx_sg *sg, aa_rx_frame_id id, double axis[3]);
+
+/* chain root -> tip (demo/domains/blocksworld/tm-blocks.py:202: aa.scene_chain(scene, "", frame));
+ * root may be AA_RX_FRAME_ROOT.  The sub-scene-graph lists the configuration variables on the chain. */
+struct aa_rx_sg_sub;
+struct aa_rx_sg_sub *aa_rx_sg_chain_create(const struct aa_rx_sg *sg, aa_rx_frame_id root, aa_rx_frame_id tip);
+void aa_rx_sg_sub_destroy(struct aa_rx_sg_sub *ssg);
+size_t aa_rx_sg_sub_config_count(const struct aa_rx_sg_sub *ssg);
+const aa_rx_config_id *aa_rx_sg_sub_configs(const struct aa_rx_sg_sub *ssg);
+aa_rx_frame_id aa_rx_sg_sub_tip(const struct aa_rx_sg_sub *ssg);
+
+/* One motion query: RRT-Connect over the sub-scene-graph's joints (bounds = joint limits, range =
+ * 20 % and edge resolution = 1 % of the state-space extent: the OMPL defaults) with
+ * every extension checked through aa_rx_cl_check_edges, many extensions per call. */
+struct aa_rx_mp;
+struct aa_rx_mp *aa_rx_mp_create(const struct aa_rx_sg_sub *ssg);
+void aa_rx_mp_destroy(struct aa_rx_mp *mp);
+/* start configuration (all n_all variables); collisions present at the start are allowed, as Amino does */
+void aa_rx_mp_set_start(struct aa_rx_mp *mp, size_t n_all, const double *q_all);
+/* workspace goal for the tip frame (7 doubles): inverse kinematics from several seeds, solutions that
+ * violate limits or collide are dropped.  Returns the number of joint-space goals found (0 = failure). */
+int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7);
+/* joint-space goal (n_sub values); returns 1 if it is valid */
+int aa_rx_mp_set_goal(struct aa_rx_mp *mp, size_t n_sub, const double *q_sub);
+void aa_rx_mp_set_simplify(struct aa_rx_mp *mp, int simplify);
+void aa_rx_mp_set_track_collisions(struct aa_rx_mp *mp, int track);
+void aa_rx_mp_set_seed(struct aa_rx_mp *mp, uint64_t seed);
+/* Plan.  On success returns 0 and a malloc'ed path of *n_path rows x n_all doubles (caller frees);
+ * on failure (timeout in seconds reached, no goal) returns -1 (-> planning-failure, lisp/tm-plan.lisp:3-7). */
+int aa_rx_mp_plan(struct aa_rx_mp *mp, double timeout, size_t *n_path, double **path_all);
+/* frame pairs that blocked extensions of the last query (the :collision constraint feed-back) */
+void aa_rx_mp_collisions(struct aa_rx_mp *mp, struct aa_rx_cl_set *set);
+struct tmk_mp_stats {
+    uint64_t n_iterations, n_edge_calls, n_edges_checked, n_nodes, n_ik_iterations, n_goals;
+    double ik_s, rrt_s, simplify_s;
+};
+void aa_rx_mp_stats(const struct aa_rx_mp *mp, struct tmk_mp_stats *out);
+
+/* Plan files (doc/md/planfile.md:13-76; grammar src/planfile.l:77-192): line-based text,
+ * "a ACTION args..", "r frame new_parent", "m config names..", "p values..", "# comment". */
+struct tmk_plan;
+struct tmk_plan *tmk_plan_create(void);
+void tmk_plan_destroy(struct tmk_plan *p);
+void tmk_plan_add_action(struct tmk_plan *p, const char *text);
+void tmk_plan_add_reparent(struct tmk_plan *p, const char *frame, const char *new_parent);
+void tmk_plan_add_motion(struct tmk_plan *p, size_t n_names, const char *const *names, size_t n_points, const double *points,
+                         size_t ld);
+/* 0 on success; -1 + message on stderr otherwise (src/tmplan.c:301-305 convention) */
+int tmk_plan_write(const struct tmk_plan *p, const char *path);
+struct tmk_plan *tmk_plan_parse(const char *path);
+size_t tmk_plan_op_count(const struct tmk_plan *p);
+/* kind: 'a', 'r' or 'm' */
+int tmk_plan_op_kind(const struct tmk_plan *p, size_t i);
+/* 'a': the action text | 'r': k = 0 frame, 1 new parent | 'm': the k-th configuration name */
+const char *tmk_plan_op_text(const struct tmk_plan *p, size_t i, size_t k);
+size_t tmk_plan_motion_names(const struct tmk_plan *p, size_t i);
+size_t tmk_plan_motion_points(const struct tmk_plan *p, size_t i);
+const double *tmk_plan_motion_data(const struct tmk_plan *p, size_t i); /* points x names, dense */
+
 /* Device-time instrumentation for bench.py's roofline: while enabled, CUDA events are recorded on
  * the launching stream around the main validity kernel and around the double-precision re-check
  * kernel of every batch.  aa_rx_cl_kernel_time synchronises those events, returns the number of

@@ -1,0 +1,145 @@
+"""The caller of the path: workspace-goal IK, RRT-Connect on the batched edge
+entry point, shortcut simplification, reparenting, plan-file output - on the Baxter Sussman problem
+(reference demo/baxter-sussman; refinement semantics demo/domains/blocksworld/tm-blocks.py:200-266).
+Every returned path is re-validated against the CPU oracle at OMPL resolution."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tmkit_b200 import amino as A
+from tmkit_b200 import scenes as S
+from tmkit_b200 import sussman as SU
+from tmkit_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+CORES = os.cpu_count() or 1
+
+
+def _validate_path(desc, path, names, goal=None):
+    orc = O.OracleScene(S.flatten(desc))
+    assert orc.config_names == desc.config_names()
+    orc.allow_config(path[0])  # start-state allowance
+    sub = orc.config_ids(names)
+    lim = W.arm_limit_table(names)
+    assert (path[:, sub] >= lim[:, 0] - 1e-9).all() and (path[:, sub] <= lim[:, 1] + 1e-9).all()
+    others = np.setdiff1d(np.arange(path.shape[1]), sub)
+    assert np.array_equal(path[:, others], np.repeat(path[:1, others], len(path), axis=0))
+    st, ex, first, _ = orc.check_edges(sub, path[0], path[:-1, sub], path[1:, sub], W.seg_len(lim), threads=CORES)
+    assert (st != O.HIT).all(), f"path edge {np.nonzero(st == O.HIT)[0]} collides according to the oracle"
+    return orc
+
+
+def test_joint_goal_query(built):
+    sc = S.baxter_sussman()
+    sg = A.SceneGraph.from_scene(sc)
+    q0 = S.q0_vector(sc)
+    ssg = A.SubSceneGraph(sg, "", SU.FRAME)
+    assert ssg.config_names() == S.RIGHT_ARM
+    mp = A.MotionPlanner(ssg)
+    mp.set_simplify(True)
+    mp.set_start(q0)
+    goal = q0[ssg.config_ids()].copy()
+    goal[0] -= 1.2  # swing the shoulder: blocked by nothing or by the table, either way a path exists
+    goal[1] -= 0.3
+    assert mp.set_goal(goal) == 1
+    path = mp.plan(3.0)
+    assert path is not None and len(path) >= 2
+    np.testing.assert_array_equal(path[0], q0)
+    np.testing.assert_allclose(path[-1][ssg.config_ids()], goal)
+    _validate_path(sc, path, S.RIGHT_ARM)
+    # an invalid goal is refused: arm through the table
+    bad = q0[ssg.config_ids()].copy()
+    bad[1] = 1.0
+    bad[3] = 0.0
+    if mp.set_goal(bad) == 0:
+        mp2 = A.MotionPlanner(ssg)
+        mp2.set_start(q0)
+        assert mp2.set_goal(bad) == 0 and mp2.plan(0.2) is None  # no goal -> planning failure
+
+
+def test_workspace_goal_ik(built):
+    sc = S.baxter_sussman()
+    sg = A.SceneGraph.from_scene(sc)
+    q0 = S.q0_vector(sc)
+    _, ab = sg.tf(q0)
+    ssg = A.SubSceneGraph(sg, "", SU.FRAME)
+    mp = A.MotionPlanner(ssg)
+    mp.set_start(q0)
+    goal = ab[sg.frame_id("block_c")]
+    assert mp.set_wsgoal(goal) >= 1
+    path = mp.plan(3.0)
+    assert path is not None
+    _, ab1 = sg.tf(path[-1])
+    tip = ab1[sg.frame_id(SU.FRAME)]
+    assert np.abs(tip[4:] - goal[4:]).max() < 1e-6
+    assert min(np.abs(tip[:4] - goal[:4]).max(), np.abs(tip[:4] + goal[:4]).max()) < 1e-6
+    # unreachable goal: 3 m away
+    far = goal.copy()
+    far[4] += 3.0
+    mp.set_start(q0)
+    assert mp.set_wsgoal(far) == 0 and mp.plan(0.2) is None
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_sussman_end_to_end(built, tmp_path, seed):
+    r = SU.run(seed=seed)
+    assert r.ok, f"planning failure at {r.failed_action}"
+    assert len(r.paths) == 6
+    for k, (path, desc, (tip, goal)) in enumerate(zip(r.paths, r.scene_descs, r.goals)):
+        orc = _validate_path(desc, path, S.RIGHT_ARM)
+        if k:
+            np.testing.assert_array_equal(path[0], r.paths[k - 1][-1])  # each query starts where the last one ended
+        tipf = orc.fk(path[-1])[1][orc.frame_id(tip)]
+        assert np.abs(tipf[4:] - goal[4:]).max() < 1e-6, (k, tip)
+    # goal of the anomaly: A on B on C, each 1e-4 m above what carries it, all above the table
+    orc = O.OracleScene(S.flatten(r.scene_final))
+    ab = orc.fk(r.q_final)[1]
+    za, zb, zc = (ab[orc.frame_id(n)][6] for n in ("block_a", "block_b", "block_c"))
+    assert zb - zc == pytest.approx(0.1001, abs=1e-6) and za - zb == pytest.approx(0.1001, abs=1e-6)
+    for n in ("block_a", "block_b"):
+        assert np.abs(ab[orc.frame_id(n)][4:6] - ab[orc.frame_id("block_c")][4:6]).max() < 1e-6
+    assert orc.flat["parent"][orc.frame_id("block_a")] == orc.frame_id("block_b")
+    assert orc.flat["parent"][orc.frame_id("block_b")] == orc.frame_id("block_c")
+    assert orc.flat["parent"][orc.frame_id("block_c")] == orc.frame_id("front_table")
+    # plan file: 6 x (action, motion, reparent), replayable
+    f = tmp_path / "sussman.tmp"
+    assert r.plan.write(str(f)) == 0
+    ops = A.PlanFile.parse(str(f)).ops()
+    assert [o[0] for o in ops] == ["a", "m", "r"] * 6
+    assert ops[0][1] == "UNSTACK block_c block_a" and ops[2] == ("r", "block_c", SU.FRAME)
+    assert ops[1][1] == S.RIGHT_ARM
+    for k in range(6):
+        np.testing.assert_array_equal(ops[3 * k + 1][2], r.paths[k][:, orc.config_ids(S.RIGHT_ARM)])
+    assert r.times["total"] < 6 * SU.MOTION_TIMEOUT
+
+
+def test_collision_feedback(built):
+    """:track-collisions - the frame pairs that blocked extensions (lisp/itmp-rec.lisp:230-247)."""
+    sc = S.baxter_sussman()
+    sg = A.SceneGraph.from_scene(sc)
+    q0 = S.q0_vector(sc)
+    ssg = A.SubSceneGraph(sg, "", SU.FRAME)
+    ids = ssg.config_ids()
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    sg.allow_config(q0)
+    cl = A.Collision(sg)
+    cand = W.random_configs(lim, 400, seed=12)
+    cand = cand[cl.check_batch(ids, q0, cand)]
+    for goal in cand:
+        mp = A.MotionPlanner(ssg)
+        mp.set_track_collisions(True)
+        mp.set_start(q0)
+        assert mp.set_goal(goal) == 1
+        path = mp.plan(0.5)
+        if mp.stats().n_iterations == 0:
+            continue  # straight line was free: nothing was blocked
+        # (a sampled goal may lie in another component of the free space, e.g. under the table:
+        # then the query times out, which is the planning-failure the task planner reacts to)
+        pairs = mp.collisions().pairs()
+        assert len(pairs) > 0
+        names = {sg.frame_name(i) for p in pairs for i in p}
+        assert any(n.startswith("right_") for n in names)
+        return
+    pytest.fail("every sampled goal was directly reachable")

@@ -425,9 +425,11 @@ def test_blocksworld_scaling_scenes(n_blocks):
     assert 0.02 < valid.mean() < 0.98
 
 
-def test_dual_arm_clutter_scene():
-    """14 varied joints, 128 random primitives (boxes / cylinders / spheres)."""
-    sc = S.clutter_scene(128, seed=1)
+@pytest.mark.parametrize("n_prims", [128, 512])
+def test_dual_arm_clutter_scene(n_prims):
+    """14 varied joints, random primitives (boxes / cylinders / spheres); 512 = BASELINE configs[4]
+    (20 moving geometries, ~10K candidate pairs: the image is read through L1, not staged)."""
+    sc = S.clutter_scene(n_prims, seed=1)
     q0 = S.q0_vector(sc)
     sg, cl, _ = _gpu_scene(sc, q0)
     orc = _oracle_scene(sc, q0)

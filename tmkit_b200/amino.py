@@ -86,6 +86,38 @@ SIGNATURES = {
     "aa_rx_cl_batch_collisions": (None, [_vp, _vp]),
     "aa_rx_cl_batch_stats": (None, [_vp, _vp]),
     "aa_rx_cl_stats_enable": (None, [_vp, _i]),
+    "aa_rx_sg_frame_type": (_i, [_vp, _i]),
+    "aa_rx_sg_frame_config": (_i, [_vp, _i]),
+    "aa_rx_sg_frame_axis": (None, [_vp, _i, _vp]),
+    "aa_rx_sg_chain_create": (_vp, [_vp, _i, _i]),
+    "aa_rx_sg_sub_destroy": (None, [_vp]),
+    "aa_rx_sg_sub_config_count": (_sz, [_vp]),
+    "aa_rx_sg_sub_configs": (_vp, [_vp]),
+    "aa_rx_sg_sub_tip": (_i, [_vp]),
+    "aa_rx_mp_create": (_vp, [_vp]),
+    "aa_rx_mp_destroy": (None, [_vp]),
+    "aa_rx_mp_set_start": (None, [_vp, _sz, _vp]),
+    "aa_rx_mp_set_wsgoal": (_i, [_vp, _vp]),
+    "aa_rx_mp_set_goal": (_i, [_vp, _sz, _vp]),
+    "aa_rx_mp_set_simplify": (None, [_vp, _i]),
+    "aa_rx_mp_set_track_collisions": (None, [_vp, _i]),
+    "aa_rx_mp_set_seed": (None, [_vp, C.c_uint64]),
+    "aa_rx_mp_plan": (_i, [_vp, _d, _vp, _vp]),
+    "aa_rx_mp_collisions": (None, [_vp, _vp]),
+    "aa_rx_mp_stats": (None, [_vp, _vp]),
+    "tmk_plan_create": (_vp, []),
+    "tmk_plan_destroy": (None, [_vp]),
+    "tmk_plan_add_action": (None, [_vp, _cs]),
+    "tmk_plan_add_reparent": (None, [_vp, _cs, _cs]),
+    "tmk_plan_add_motion": (None, [_vp, _sz, _vp, _sz, _vp, _sz]),
+    "tmk_plan_write": (_i, [_vp, _cs]),
+    "tmk_plan_parse": (_vp, [_cs]),
+    "tmk_plan_op_count": (_sz, [_vp]),
+    "tmk_plan_op_kind": (_i, [_vp, _sz]),
+    "tmk_plan_op_text": (_cs, [_vp, _sz, _sz]),
+    "tmk_plan_motion_names": (_sz, [_vp, _sz]),
+    "tmk_plan_motion_points": (_sz, [_vp, _sz]),
+    "tmk_plan_motion_data": (_vp, [_vp, _sz]),
     "aa_rx_cl_kernel_timing": (None, [_vp, _i]),
     "aa_rx_cl_kernel_time": (_sz, [_vp, _vp, _vp]),
     "tmk_fp32_peak_tflops": (_d, []),
@@ -442,6 +474,151 @@ class Collision:
         try:
             if self.h:
                 self.L.aa_rx_cl_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class MpStats(C.Structure):
+    _fields_ = [("n_iterations", C.c_uint64), ("n_edge_calls", C.c_uint64), ("n_edges_checked", C.c_uint64),
+                ("n_nodes", C.c_uint64), ("n_ik_iterations", C.c_uint64), ("n_goals", C.c_uint64),
+                ("ik_s", C.c_double), ("rrt_s", C.c_double), ("simplify_s", C.c_double)]
+
+
+class SubSceneGraph:
+    """struct aa_rx_sg_sub: the chain root -> tip (tm-blocks.py:202 aa.scene_chain)."""
+
+    def __init__(self, sg: SceneGraph, root: str, tip: str):
+        self.L = lib()
+        self.sg = sg
+        r = -1 if root == "" else sg.frame_id(root)
+        self.h = self.L.aa_rx_sg_chain_create(sg.h, r, sg.frame_id(tip))
+
+    def config_ids(self) -> np.ndarray:
+        n = self.L.aa_rx_sg_sub_config_count(self.h)
+        p = C.cast(self.L.aa_rx_sg_sub_configs(self.h), C.POINTER(C.c_int))
+        return np.asarray([p[i] for i in range(n)], dtype=np.int32)
+
+    def config_names(self):
+        return [self.sg.config_name(int(i)) for i in self.config_ids()]
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.aa_rx_sg_sub_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class MotionPlanner:
+    """struct aa_rx_mp: what robray:motion-plan drives (lisp/python/tmsmtpy.lisp:55-60)."""
+
+    def __init__(self, ssg: SubSceneGraph):
+        self.L = lib()
+        self.ssg = ssg
+        self.h = self.L.aa_rx_mp_create(ssg.h)
+
+    def set_start(self, q_all):
+        q = _f64(q_all)
+        self.L.aa_rx_mp_set_start(self.h, len(q), _p(q))
+
+    def set_wsgoal(self, tf7) -> int:
+        e = _f64(tf7)
+        return self.L.aa_rx_mp_set_wsgoal(self.h, _p(e))
+
+    def set_goal(self, q_sub) -> int:
+        q = _f64(q_sub)
+        return self.L.aa_rx_mp_set_goal(self.h, len(q), _p(q))
+
+    def set_simplify(self, on: bool = True):
+        self.L.aa_rx_mp_set_simplify(self.h, int(on))
+
+    def set_track_collisions(self, on: bool = True):
+        self.L.aa_rx_mp_set_track_collisions(self.h, int(on))
+
+    def set_seed(self, seed: int):
+        self.L.aa_rx_mp_set_seed(self.h, seed)
+
+    def plan(self, timeout: float = 3.0):
+        """returns the path (n_points x n_all) or None on planning failure."""
+        n = C.c_size_t(0)
+        ptr = C.c_void_p(0)
+        rc = self.L.aa_rx_mp_plan(self.h, float(timeout), C.byref(n), C.byref(ptr))
+        if rc != 0:
+            return None
+        n_all = self.ssg.sg.config_count()
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n.value, n_all)).copy()
+        C.CDLL(None).free(ptr)
+        return arr
+
+    def collisions(self) -> CollisionSet:
+        s = CollisionSet(self.ssg.sg)
+        self.L.aa_rx_mp_collisions(self.h, s.h)
+        return s
+
+    def stats(self) -> MpStats:
+        st = MpStats()
+        self.L.aa_rx_mp_stats(self.h, C.byref(st))
+        return st
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.aa_rx_mp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class PlanFile:
+    """plan files (doc/md/planfile.md)."""
+
+    def __init__(self, handle=None):
+        self.L = lib()
+        self.h = handle if handle is not None else self.L.tmk_plan_create()
+
+    @classmethod
+    def parse(cls, path: str) -> Optional["PlanFile"]:
+        h = lib().tmk_plan_parse(_b(path))
+        return cls(handle=h) if h else None
+
+    def add_action(self, text: str):
+        self.L.tmk_plan_add_action(self.h, _b(text))
+
+    def add_reparent(self, frame: str, new_parent: str):
+        self.L.tmk_plan_add_reparent(self.h, _b(frame), _b(new_parent))
+
+    def add_motion(self, names: Sequence[str], points):
+        pts = _f64(points)
+        arr = (C.c_char_p * len(names))(*[_b(n) for n in names])
+        self.L.tmk_plan_add_motion(self.h, len(names), arr, pts.shape[0], _p(pts), pts.shape[1])
+
+    def write(self, path: str) -> int:
+        return self.L.tmk_plan_write(self.h, _b(path))
+
+    def ops(self):
+        out = []
+        for i in range(self.L.tmk_plan_op_count(self.h)):
+            kind = chr(self.L.tmk_plan_op_kind(self.h, i))
+            if kind == "a":
+                out.append(("a", self.L.tmk_plan_op_text(self.h, i, 0).decode()))
+            elif kind == "r":
+                out.append(("r", self.L.tmk_plan_op_text(self.h, i, 0).decode(), self.L.tmk_plan_op_text(self.h, i, 1).decode()))
+            else:
+                nn, npt = self.L.tmk_plan_motion_names(self.h, i), self.L.tmk_plan_motion_points(self.h, i)
+                names = [self.L.tmk_plan_op_text(self.h, i, k).decode() for k in range(nn)]
+                data = np.zeros((npt, nn))
+                if npt:
+                    p = C.cast(self.L.tmk_plan_motion_data(self.h, i), C.POINTER(C.c_double))
+                    data = np.ctypeslib.as_array(p, shape=(npt, nn)).copy()
+                out.append(("m", names, data))
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.tmk_plan_destroy(self.h)
                 self.h = None
         except Exception:
             pass

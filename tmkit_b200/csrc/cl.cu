@@ -53,6 +53,7 @@ template <typename T> static void upload(DBuf &b, const std::vector<T> &v, cudaS
 /* ------------------------------------------------------------------ scene-graph device mirror (FK) */
 struct SgDev {
     DBuf frames, q, rel, ab;
+    DBuf b_frames, b_q, b_out; /* aa_rx_sg_tf_batch scratch (kept: IK calls it once per iteration) */
     size_t n_f = 0;
 };
 
@@ -60,6 +61,7 @@ extern "C" void tmk_dev_sg_release(void *dev) {
     SgDev *d = (SgDev *)dev;
     if (!d) return;
     d->frames.release(); d->q.release(); d->rel.release(); d->ab.release();
+    d->b_frames.release(); d->b_q.release(); d->b_out.release();
     delete d;
 }
 
@@ -1051,15 +1053,15 @@ extern "C" void aa_rx_sg_tf_batch(const struct aa_rx_sg *sg, size_t n_cfg, size_
     const int T = 64;
     size_t smem = ((sizeof(FFrame) * n_f + 15) & ~(size_t)15) + sizeof(float) * 7 * n_f * T;
     if (smem > 200 * 1024) tmk_die("aa_rx_sg_tf_batch: %zu frames exceed the shared-memory slab", n_f);
-    DBuf dfr, dq, dout;
+    SgDev *sd = sg_dev(sg);
+    DBuf &dfr = sd->b_frames, &dq = sd->b_q, &dout = sd->b_out;
     upload(dfr, fr, 0);
     dq.need(n_cfg * ldQ * 8);
-    CK(cudaMemcpy(dq.p, Q_sub, n_cfg * ldQ * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(dq.p, Q_sub, n_cfg * ldQ * 8, cudaMemcpyHostToDevice, 0));
     dout.need(n_cfg * n_out * 7 * 8);
     CK(cudaFuncSetAttribute(k_fk_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fk_batch<<<(unsigned)((n_cfg + T - 1) / T), T, smem>>>((const FFrame *)dfr.p, (int)n_f, (const double *)dq.p, ldQ,
                                                              n_cfg, (int)n_out, (double *)dout.p);
     CK(cudaGetLastError());
     CK(cudaMemcpy(TF_abs_out, dout.p, n_cfg * n_out * 7 * 8, cudaMemcpyDeviceToHost));
-    dfr.release(); dq.release(); dout.release();
 }

@@ -1,0 +1,541 @@
+/* mp.c - one motion query on top of the batched validity check: workspace-goal IK, RRT-Connect,
+ * shortcut simplification.  Host C; every state / edge validity decision goes through the C ABI
+ * (aa_rx_cl_check_batch, aa_rx_cl_check_edges), i.e. through the CUDA kernels.
+ *
+ * What it stands in for (all external to the reference tree):
+ *   robray:motion-plan  ->  aa_rx_mp_create / set_start / set_wsgoal / set_simplify /
+ *   set_track_collisions / aa_rx_mp_plan(timeout)        lisp/python/tmsmtpy.lisp:55-60
+ *   OMPL RRTConnect (range = 20 % of the state-space extent), DiscreteMotionValidator
+ *   (resolution = 1 % of the extent) and PathSimplifier.
+ * The planner is frontier-parallel: every iteration proposes K extensions and checks them, and
+ * the K connection attempts that follow, with one aa_rx_cl_check_edges call each.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "tmk_internal.h"
+
+#define MP_K 128        /* extensions proposed per iteration */
+#define MP_IK_SEEDS 48
+#define MP_IK_ITERS 120
+#define MP_MAX_GOALS 16
+#define MP_MAX_BLOCKED 2048
+
+typedef struct {
+    size_t n, cap, dim;
+    double *q;   /* n x dim */
+    int *parent; /* -1 = root */
+} tree;
+
+struct aa_rx_mp {
+    const struct aa_rx_sg_sub *ssg;
+    const struct aa_rx_sg *sg;
+    size_t n_all, n_sub;
+    const aa_rx_config_id *ids;
+    double *lo, *hi;
+    double extent, range, seg_len;
+    double *q_start_all;
+    int have_start;
+    struct aa_rx_cl *cl;
+    size_t n_goal;
+    double goals[MP_MAX_GOALS][TMK_MP_MAXSUB];
+    int simplify, track;
+    uint64_t rng;
+    size_t n_blocked;
+    double *blocked; /* end points of rejected extensions (for the collision feed-back) */
+    struct tmk_mp_stats st;
+};
+
+static double now_s(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+static uint64_t rng_next(uint64_t *s) { /* splitmix64 */
+    uint64_t z = (*s += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+static double rng_unit(uint64_t *s) { return (double)(rng_next(s) >> 11) * (1.0 / 9007199254740992.0); }
+
+static double dist(const double *a, const double *b, size_t n) {
+    double s = 0;
+    for (size_t k = 0; k < n; k++) s += (a[k] - b[k]) * (a[k] - b[k]);
+    return sqrt(s);
+}
+
+static void tree_init(tree *t, size_t dim) { memset(t, 0, sizeof(*t)); t->dim = dim; }
+static void tree_free(tree *t) { free(t->q); free(t->parent); }
+static int tree_add(tree *t, const double *q, int parent) {
+    if (t->n == t->cap) {
+        t->cap = t->cap ? 2 * t->cap : 256;
+        t->q = (double *)realloc(t->q, sizeof(double) * t->cap * t->dim);
+        t->parent = (int *)realloc(t->parent, sizeof(int) * t->cap);
+    }
+    memcpy(t->q + t->n * t->dim, q, sizeof(double) * t->dim);
+    t->parent[t->n] = parent;
+    return (int)t->n++;
+}
+static int tree_nearest(const tree *t, const double *q, double *d_out) {
+    int best = 0;
+    double bd = INFINITY;
+    for (size_t i = 0; i < t->n; i++) {
+        double s = 0;
+        const double *p = t->q + i * t->dim;
+        for (size_t k = 0; k < t->dim; k++) s += (p[k] - q[k]) * (p[k] - q[k]);
+        if (s < bd) { bd = s; best = (int)i; }
+    }
+    if (d_out) *d_out = sqrt(bd);
+    return best;
+}
+
+/* ------------------------------------------------------------------ create / destroy / options */
+struct aa_rx_mp *aa_rx_mp_create(const struct aa_rx_sg_sub *ssg) {
+    struct aa_rx_mp *mp = (struct aa_rx_mp *)calloc(1, sizeof(*mp));
+    mp->ssg = ssg;
+    mp->sg = tmk_sub_sg(ssg);
+    mp->n_all = aa_rx_sg_config_count(mp->sg);
+    mp->n_sub = aa_rx_sg_sub_config_count(ssg);
+    mp->ids = aa_rx_sg_sub_configs(ssg);
+    if (mp->n_sub < 1) tmk_die("aa_rx_mp_create: the sub-scene-graph has no configuration variable");
+    if (mp->n_sub > TMK_MP_MAXSUB) tmk_die("aa_rx_mp_create: %zu configuration variables > %d", mp->n_sub, TMK_MP_MAXSUB);
+    mp->lo = (double *)malloc(sizeof(double) * mp->n_sub);
+    mp->hi = (double *)malloc(sizeof(double) * mp->n_sub);
+    double e2 = 0;
+    for (size_t k = 0; k < mp->n_sub; k++) {
+        if (aa_rx_sg_get_limit_pos(mp->sg, mp->ids[k], &mp->lo[k], &mp->hi[k]) != 0) { mp->lo[k] = -M_PI; mp->hi[k] = M_PI; }
+        e2 += (mp->hi[k] - mp->lo[k]) * (mp->hi[k] - mp->lo[k]);
+    }
+    mp->extent = sqrt(e2);
+    mp->range = 0.2 * mp->extent;    /* OMPL RRTConnect default range */
+    mp->seg_len = 0.01 * mp->extent; /* longestValidSegmentFraction */
+    mp->q_start_all = (double *)calloc(mp->n_all + 1, sizeof(double));
+    mp->simplify = 0;
+    mp->rng = 0x1234567ull;
+    mp->blocked = (double *)malloc(sizeof(double) * MP_MAX_BLOCKED * mp->n_sub);
+    return mp;
+}
+
+void aa_rx_mp_destroy(struct aa_rx_mp *mp) {
+    if (!mp) return;
+    if (mp->cl) aa_rx_cl_destroy(mp->cl);
+    free(mp->lo); free(mp->hi); free(mp->q_start_all); free(mp->blocked);
+    free(mp);
+}
+
+void aa_rx_mp_set_simplify(struct aa_rx_mp *mp, int simplify) { mp->simplify = simplify; }
+void aa_rx_mp_set_track_collisions(struct aa_rx_mp *mp, int track) { mp->track = track; }
+void aa_rx_mp_set_seed(struct aa_rx_mp *mp, uint64_t seed) { mp->rng = seed * 0x9e3779b97f4a7c15ull + 1; }
+void aa_rx_mp_stats(const struct aa_rx_mp *mp, struct tmk_mp_stats *out) { *out = mp->st; }
+
+/* start configuration; what collides there is allowed for this query (in-tree
+ * analogue demo/tmpexec.c:118) */
+void aa_rx_mp_set_start(struct aa_rx_mp *mp, size_t n_all, const double *q_all) {
+    if (n_all != mp->n_all) tmk_die("aa_rx_mp_set_start: n_all = %zu, scene graph has %zu", n_all, mp->n_all);
+    memcpy(mp->q_start_all, q_all, sizeof(double) * n_all);
+    if (mp->cl) aa_rx_cl_destroy(mp->cl);
+    mp->cl = aa_rx_cl_create(mp->sg);
+    size_t n_f = aa_rx_sg_frame_count(mp->sg);
+    double *ab = (double *)malloc(sizeof(double) * 7 * (n_f + 1));
+    aa_rx_sg_tf(mp->sg, n_all, q_all, n_f, NULL, 7, ab, 7);
+    struct aa_rx_cl_set *set = aa_rx_cl_set_create(mp->sg);
+    if (aa_rx_cl_check(mp->cl, n_f, ab, 7, set)) aa_rx_cl_allow_set(mp->cl, set);
+    aa_rx_cl_set_destroy(set);
+    free(ab);
+    mp->have_start = 1;
+    mp->n_goal = 0;
+    memset(&mp->st, 0, sizeof(mp->st));
+}
+
+static int in_limits(const struct aa_rx_mp *mp, const double *q) {
+    for (size_t k = 0; k < mp->n_sub; k++)
+        if (q[k] < mp->lo[k] - 1e-9 || q[k] > mp->hi[k] + 1e-9) return 0;
+    return 1;
+}
+
+static int config_valid(struct aa_rx_mp *mp, const double *q_sub) {
+    uint32_t bits[2] = {0, 0};
+    aa_rx_cl_check_batch(mp->cl, 1, mp->n_sub, mp->ids, mp->n_all, mp->q_start_all, q_sub, mp->n_sub, bits);
+    return (int)(bits[0] & 1u);
+}
+
+int aa_rx_mp_set_goal(struct aa_rx_mp *mp, size_t n_sub, const double *q_sub) {
+    if (!mp->have_start) tmk_die("aa_rx_mp_set_goal: set the start first");
+    if (n_sub != mp->n_sub) tmk_die("aa_rx_mp_set_goal: n_sub mismatch");
+    if (!in_limits(mp, q_sub) || !config_valid(mp, q_sub)) return 0;
+    if (mp->n_goal < MP_MAX_GOALS) memcpy(mp->goals[mp->n_goal++], q_sub, sizeof(double) * n_sub);
+    mp->st.n_goals = mp->n_goal;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ inverse kinematics */
+/* solve (A + lambda^2 I) x = b for symmetric positive definite 6x6 A (Cholesky) */
+static int solve6(double A[6][6], const double *b, double lambda2, double *x) {
+    double L[6][6];
+    memset(L, 0, sizeof(L));
+    for (int i = 0; i < 6; i++) {
+        for (int j = 0; j <= i; j++) {
+            double s = A[i][j] + (i == j ? lambda2 : 0.0);
+            for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+            if (i == j) {
+                if (s <= 0) return -1;
+                L[i][i] = sqrt(s);
+            } else L[i][j] = s / L[j][j];
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; i++) {
+        double s = b[i];
+        for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+        y[i] = s / L[i][i];
+    }
+    for (int i = 5; i >= 0; i--) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
+        x[i] = s / L[i][i];
+    }
+    return 0;
+}
+
+/* pose error of tip vs goal (6-vector: translation, rotation vector) */
+static void pose_error(const double *tip, const double *goal, double *e) {
+    for (int k = 0; k < 3; k++) e[k] = goal[4 + k] - tip[4 + k];
+    double c[4] = {-tip[0], -tip[1], -tip[2], tip[3]}, d[4];
+    tmk_qmul(goal, c, d); /* goal * conj(tip) */
+    double sgn = d[3] < 0 ? -1.0 : 1.0;
+    double vn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    double ang = 2.0 * atan2(vn, sgn * d[3]);
+    double sc = vn > 1e-12 ? sgn * ang / vn : 2.0 * sgn;
+    for (int k = 0; k < 3; k++) e[3 + k] = sc * d[k];
+}
+
+/* one damped-least-squares step for one candidate from the absolute poses of the chain frames */
+static void ik_step(const struct aa_rx_mp *mp, size_t n_fr, const aa_rx_frame_id *frames, const double *tf /* n_fr x 7 */,
+                    const double *goal, double *q, double *err_p, double *err_o) {
+    const double *tip = tf + 7 * (n_fr - 1);
+    double e[6];
+    pose_error(tip, goal, e);
+    *err_p = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    *err_o = sqrt(e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
+    double J[6][TMK_MP_MAXSUB];
+    memset(J, 0, sizeof(J));
+    for (size_t f = 0; f < n_fr; f++) {
+        int type = aa_rx_sg_frame_type(mp->sg, frames[f]);
+        if (type == TMK_FIXED) continue;
+        int cid = aa_rx_sg_frame_config(mp->sg, frames[f]);
+        size_t col = 0;
+        while (col < mp->n_sub && mp->ids[col] != cid) col++;
+        if (col == mp->n_sub) continue;
+        double ax[3], aw[3];
+        aa_rx_sg_frame_axis(mp->sg, frames[f], ax);
+        double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        for (int k = 0; k < 3; k++) ax[k] /= an;
+        const double *F = tf + 7 * f;
+        tmk_qrot(F, ax, aw);
+        if (type == TMK_REVOLUTE) {
+            double r[3] = {tip[4] - F[4], tip[5] - F[5], tip[6] - F[6]};
+            J[0][col] += aw[1] * r[2] - aw[2] * r[1];
+            J[1][col] += aw[2] * r[0] - aw[0] * r[2];
+            J[2][col] += aw[0] * r[1] - aw[1] * r[0];
+            for (int k = 0; k < 3; k++) J[3 + k][col] += aw[k];
+        } else {
+            for (int k = 0; k < 3; k++) J[k][col] += aw[k];
+        }
+    }
+    double A[6][6];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            double s = 0;
+            for (size_t k = 0; k < mp->n_sub; k++) s += J[i][k] * J[j][k];
+            A[i][j] = s;
+        }
+    double en = *err_p + *err_o;
+    double lambda2 = fmin(1e-2, 1e-2 * en * en) + 1e-9; /* damping shrinks as the solution is approached */
+    double y[6];
+    if (solve6(A, e, lambda2, y) != 0) return;
+    double big = 0, dq[TMK_MP_MAXSUB];
+    for (size_t k = 0; k < mp->n_sub; k++) {
+        double s = 0;
+        for (int i = 0; i < 6; i++) s += J[i][k] * y[i];
+        dq[k] = s;
+        if (fabs(s) > big) big = fabs(s);
+    }
+    double scale = big > 0.4 ? 0.4 / big : 1.0;
+    for (size_t k = 0; k < mp->n_sub; k++) {
+        q[k] += scale * dq[k];
+        if (q[k] < mp->lo[k]) q[k] = mp->lo[k];
+        if (q[k] > mp->hi[k]) q[k] = mp->hi[k];
+    }
+}
+
+int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
+    if (!mp->have_start) tmk_die("aa_rx_mp_set_wsgoal: set the start first");
+    double t0 = now_s();
+    double goal[7];
+    memcpy(goal, E7, sizeof(goal));
+    double gn = sqrt(goal[0] * goal[0] + goal[1] * goal[1] + goal[2] * goal[2] + goal[3] * goal[3]);
+    for (int k = 0; k < 4; k++) goal[k] /= gn;
+    const aa_rx_frame_id *frames;
+    size_t n_fr = tmk_sub_frames(mp->ssg, &frames);
+    const size_t S = MP_IK_SEEDS, n = mp->n_sub;
+    double *Q = (double *)malloc(sizeof(double) * S * n);
+    double *TF = (double *)malloc(sizeof(double) * S * n_fr * 7);
+    uint8_t *done = (uint8_t *)calloc(S, 1);
+    for (size_t s = 0; s < S; s++)
+        for (size_t k = 0; k < n; k++) {
+            double q0 = mp->q_start_all[mp->ids[k]];
+            if (s == 0) Q[s * n + k] = q0;
+            else if (s < 8) { /* near the start: short motions are preferred */
+                double w = 0.15 * (double)s;
+                double v = q0 + w * (rng_unit(&mp->rng) - 0.5) * (mp->hi[k] - mp->lo[k]);
+                Q[s * n + k] = fmin(mp->hi[k], fmax(mp->lo[k], v));
+            } else Q[s * n + k] = mp->lo[k] + rng_unit(&mp->rng) * (mp->hi[k] - mp->lo[k]);
+        }
+    /* lock-step iterations: one batched FK (GPU) per iteration for all candidates */
+    size_t n_done = 0;
+    /* stop early once plenty of candidates have converged and the stragglers had their chance */
+    for (int it = 0; it < MP_IK_ITERS && n_done < S && !(n_done >= 12 && it >= 24); it++) {
+        aa_rx_sg_tf_batch(mp->sg, S, n, mp->ids, mp->n_all, mp->q_start_all, Q, n, n_fr, frames, TF);
+        mp->st.n_ik_iterations++;
+        for (size_t s = 0; s < S; s++) {
+            if (done[s]) continue;
+            double ep, eo;
+            double before[TMK_MP_MAXSUB];
+            memcpy(before, Q + s * n, sizeof(double) * n);
+            ik_step(mp, n_fr, frames, TF + s * n_fr * 7, goal, Q + s * n, &ep, &eo);
+            if (ep < 2e-5 && eo < 2e-5) { /* FP32 FK accuracy; polished in double below */
+                memcpy(Q + s * n, before, sizeof(double) * n);
+                done[s] = 1;
+                n_done++;
+            }
+        }
+    }
+    /* polish the converged candidates with the double-precision single-configuration FK */
+    size_t n_f = aa_rx_sg_frame_count(mp->sg);
+    double *ab = (double *)malloc(sizeof(double) * 7 * (n_f + 1));
+    double *chain = (double *)malloc(sizeof(double) * 7 * (n_fr + 1));
+    double *q_all = (double *)malloc(sizeof(double) * (mp->n_all + 1));
+    double cand[MP_IK_SEEDS][TMK_MP_MAXSUB];
+    double cand_cost[MP_IK_SEEDS];
+    size_t n_cand = 0;
+    for (size_t s = 0; s < S; s++) {
+        if (!done[s]) continue;
+        double *q = Q + s * n;
+        double ep = 1, eo = 1;
+        for (int it = 0; it < 6; it++) {
+            memcpy(q_all, mp->q_start_all, sizeof(double) * mp->n_all);
+            aa_rx_sg_config_set(mp->sg, mp->n_all, n, mp->ids, q, q_all);
+            aa_rx_sg_tf(mp->sg, mp->n_all, q_all, n_f, NULL, 7, ab, 7);
+            for (size_t f = 0; f < n_fr; f++) memcpy(chain + 7 * f, ab + 7 * (size_t)frames[f], sizeof(double) * 7);
+            double before[TMK_MP_MAXSUB];
+            memcpy(before, q, sizeof(double) * n);
+            ik_step(mp, n_fr, frames, chain, goal, q, &ep, &eo);
+            if (ep < 1e-9 && eo < 1e-9) { memcpy(q, before, sizeof(double) * n); break; }
+        }
+        if (ep > 1e-7 || eo > 1e-7 || !in_limits(mp, q)) continue;
+        int dup = 0;
+        for (size_t c = 0; c < n_cand; c++) dup |= dist(cand[c], q, n) < 1e-3;
+        if (dup) continue;
+        memcpy(cand[n_cand], q, sizeof(double) * n);
+        double start_sub[TMK_MP_MAXSUB];
+        for (size_t k = 0; k < n; k++) start_sub[k] = mp->q_start_all[mp->ids[k]];
+        cand_cost[n_cand] = dist(q, start_sub, n);
+        n_cand++;
+    }
+    /* collision-free candidates, nearest to the start first */
+    mp->n_goal = 0;
+    if (n_cand) {
+        uint32_t bits[(MP_IK_SEEDS + 31) / 32 + 1];
+        aa_rx_cl_check_batch(mp->cl, n_cand, n, mp->ids, mp->n_all, mp->q_start_all, &cand[0][0], TMK_MP_MAXSUB, bits);
+        for (;;) {
+            int best = -1;
+            for (size_t c = 0; c < n_cand; c++)
+                if (((bits[c >> 5] >> (c & 31)) & 1u) && (best < 0 || cand_cost[c] < cand_cost[best])) best = (int)c;
+            if (best < 0 || mp->n_goal == MP_MAX_GOALS) break;
+            memcpy(mp->goals[mp->n_goal++], cand[best], sizeof(double) * n);
+            bits[best >> 5] &= ~(1u << (best & 31));
+        }
+    }
+    free(Q); free(TF); free(done); free(ab); free(chain); free(q_all);
+    mp->st.n_goals = mp->n_goal;
+    mp->st.ik_s += now_s() - t0;
+    return (int)mp->n_goal;
+}
+
+/* ------------------------------------------------------------------ RRT-Connect, frontier-parallel */
+static size_t check_edges(struct aa_rx_mp *mp, size_t n_edge, const double *Q0, const double *Q1, uint32_t *bits) {
+    mp->st.n_edge_calls++;
+    mp->st.n_edges_checked += n_edge;
+    return aa_rx_cl_check_edges(mp->cl, n_edge, mp->n_sub, mp->ids, mp->n_all, mp->q_start_all, Q0, Q1, mp->n_sub, mp->seg_len,
+                                bits, NULL);
+}
+
+static void remember_blocked(struct aa_rx_mp *mp, const double *q) {
+    if (mp->n_blocked < MP_MAX_BLOCKED) memcpy(mp->blocked + (mp->n_blocked++) * mp->n_sub, q, sizeof(double) * mp->n_sub);
+}
+
+/* path: n x dim; returns the new length (shortest path over the vertices through valid straight edges) */
+static size_t shortcut(struct aa_rx_mp *mp, double *path, size_t n) {
+    const size_t dim = mp->n_sub;
+    if (n < 3) return n;
+    if (n > 96) return n; /* long raw paths are rare with range = 20 % of the extent */
+    size_t n_e = 0;
+    double *Q0 = (double *)malloc(sizeof(double) * dim * n * n / 2 + 8), *Q1 = (double *)malloc(sizeof(double) * dim * n * n / 2 + 8);
+    int *ei = (int *)malloc(sizeof(int) * n * n), *ej = (int *)malloc(sizeof(int) * n * n);
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = i + 2; j < n; j++) {
+            memcpy(Q0 + n_e * dim, path + i * dim, sizeof(double) * dim);
+            memcpy(Q1 + n_e * dim, path + j * dim, sizeof(double) * dim);
+            ei[n_e] = (int)i; ej[n_e] = (int)j;
+            n_e++;
+        }
+    uint32_t *bits = (uint32_t *)calloc(n_e / 32 + 2, sizeof(uint32_t));
+    check_edges(mp, n_e, Q0, Q1, bits);
+    /* DP over the DAG: consecutive edges are known valid */
+    double *cost = (double *)malloc(sizeof(double) * n);
+    int *prev = (int *)malloc(sizeof(int) * n);
+    for (size_t j = 0; j < n; j++) { cost[j] = INFINITY; prev[j] = -1; }
+    cost[0] = 0;
+    for (size_t j = 1; j < n; j++) {
+        double c = cost[j - 1] + dist(path + (j - 1) * dim, path + j * dim, dim);
+        if (c < cost[j]) { cost[j] = c; prev[j] = (int)j - 1; }
+        for (size_t e = 0; e < n_e; e++)
+            if ((size_t)ej[e] == j && ((bits[e >> 5] >> (e & 31)) & 1u)) {
+                double c2 = cost[ei[e]] + dist(path + (size_t)ei[e] * dim, path + j * dim, dim);
+                if (c2 < cost[j]) { cost[j] = c2; prev[j] = ei[e]; }
+            }
+    }
+    int *keep = (int *)malloc(sizeof(int) * n);
+    size_t m = 0;
+    for (int v = (int)n - 1; v >= 0; v = prev[v]) { keep[m++] = v; if (v == 0) break; }
+    double *out = (double *)malloc(sizeof(double) * n * dim);
+    for (size_t k = 0; k < m; k++) memcpy(out + k * dim, path + (size_t)keep[m - 1 - k] * dim, sizeof(double) * dim);
+    memcpy(path, out, sizeof(double) * m * dim);
+    free(out); free(keep); free(cost); free(prev); free(bits); free(Q0); free(Q1); free(ei); free(ej);
+    return m;
+}
+
+int aa_rx_mp_plan(struct aa_rx_mp *mp, double timeout, size_t *n_path, double **path_all) {
+    *n_path = 0;
+    *path_all = NULL;
+    if (!mp->have_start) tmk_die("aa_rx_mp_plan: set the start first");
+    if (mp->n_goal == 0) return -1;
+    const size_t dim = mp->n_sub;
+    double t0 = now_s();
+    mp->n_blocked = 0;
+    double start[TMK_MP_MAXSUB];
+    for (size_t k = 0; k < dim; k++) start[k] = mp->q_start_all[mp->ids[k]];
+
+    tree T[2]; /* T[0] grows from the start, T[1] from the goals */
+    tree_init(&T[0], dim);
+    tree_init(&T[1], dim);
+    tree_add(&T[0], start, -1);
+    for (size_t g = 0; g < mp->n_goal; g++) tree_add(&T[1], mp->goals[g], -1);
+
+    double *Q0 = (double *)malloc(sizeof(double) * MP_K * dim), *Q1 = (double *)malloc(sizeof(double) * MP_K * dim);
+    int near_idx[MP_K], new_idx[MP_K];
+    uint32_t bits[MP_K / 32 + 2];
+    int found_a = -1, found_b = -1; /* nodes of T[0] / T[1] joined by a valid straight segment */
+
+    /* the goals may be directly reachable */
+    {
+        size_t n_e = mp->n_goal;
+        for (size_t g = 0; g < n_e; g++) { memcpy(Q0 + g * dim, start, sizeof(double) * dim); memcpy(Q1 + g * dim, mp->goals[g], sizeof(double) * dim); }
+        check_edges(mp, n_e, Q0, Q1, bits);
+        for (size_t g = 0; g < n_e && found_a < 0; g++)
+            if ((bits[g >> 5] >> (g & 31)) & 1u) { found_a = 0; found_b = (int)g; }
+    }
+
+    int a = 0; /* tree being extended */
+    while (found_a < 0 && now_s() - t0 < timeout) {
+        mp->st.n_iterations++;
+        tree *Ta = &T[a], *Tb = &T[1 - a];
+        /* K extensions of Ta towards uniform samples */
+        for (int k = 0; k < MP_K; k++) {
+            double s[TMK_MP_MAXSUB], d;
+            for (size_t j = 0; j < dim; j++) s[j] = mp->lo[j] + rng_unit(&mp->rng) * (mp->hi[j] - mp->lo[j]);
+            near_idx[k] = tree_nearest(Ta, s, &d);
+            const double *nq = Ta->q + (size_t)near_idx[k] * dim;
+            double f = d > mp->range ? mp->range / d : 1.0;
+            for (size_t j = 0; j < dim; j++) {
+                Q0[k * dim + j] = nq[j];
+                Q1[k * dim + j] = nq[j] + f * (s[j] - nq[j]);
+            }
+        }
+        check_edges(mp, MP_K, Q0, Q1, bits);
+        int n_new = 0;
+        for (int k = 0; k < MP_K; k++) {
+            if ((bits[k >> 5] >> (k & 31)) & 1u) new_idx[n_new++] = tree_add(Ta, Q1 + k * dim, near_idx[k]);
+            else if (mp->track) remember_blocked(mp, Q1 + k * dim);
+        }
+        if (n_new) {
+            /* connect: straight segments from the nearest node of the other tree to every new node */
+            for (int k = 0; k < n_new; k++) {
+                const double *nq = Ta->q + (size_t)new_idx[k] * dim;
+                near_idx[k] = tree_nearest(Tb, nq, NULL);
+                memcpy(Q0 + k * dim, Tb->q + (size_t)near_idx[k] * dim, sizeof(double) * dim);
+                memcpy(Q1 + k * dim, nq, sizeof(double) * dim);
+            }
+            check_edges(mp, (size_t)n_new, Q0, Q1, bits);
+            double best = INFINITY;
+            for (int k = 0; k < n_new; k++)
+                if ((bits[k >> 5] >> (k & 31)) & 1u) {
+                    double d = dist(Q0 + k * dim, Q1 + k * dim, dim);
+                    if (d < best) {
+                        best = d;
+                        if (a == 0) { found_a = new_idx[k]; found_b = near_idx[k]; }
+                        else { found_a = near_idx[k]; found_b = new_idx[k]; }
+                    }
+                }
+        }
+        a = 1 - a;
+    }
+    mp->st.n_nodes = T[0].n + T[1].n;
+    mp->st.rrt_s += now_s() - t0;
+    int rc = -1;
+    if (found_a >= 0) {
+        /* start -> found_a (reverse of the parent walk), then found_b -> its goal root */
+        size_t na = 0, nb = 0;
+        for (int v = found_a; v >= 0; v = T[0].parent[v]) na++;
+        for (int v = found_b; v >= 0; v = T[1].parent[v]) nb++;
+        size_t n = na + nb;
+        double *path = (double *)malloc(sizeof(double) * (n + 1) * dim);
+        size_t k = na;
+        for (int v = found_a; v >= 0; v = T[0].parent[v]) memcpy(path + (--k) * dim, T[0].q + (size_t)v * dim, sizeof(double) * dim);
+        k = na;
+        for (int v = found_b; v >= 0; v = T[1].parent[v]) memcpy(path + (k++) * dim, T[1].q + (size_t)v * dim, sizeof(double) * dim);
+        if (mp->simplify) {
+            double ts = now_s();
+            n = shortcut(mp, path, n);
+            mp->st.simplify_s += now_s() - ts;
+        }
+        double *out = (double *)malloc(sizeof(double) * n * mp->n_all);
+        for (size_t i = 0; i < n; i++) {
+            memcpy(out + i * mp->n_all, mp->q_start_all, sizeof(double) * mp->n_all);
+            aa_rx_sg_config_set(mp->sg, mp->n_all, dim, mp->ids, path + i * dim, out + i * mp->n_all);
+        }
+        free(path);
+        *n_path = n;
+        *path_all = out;
+        rc = 0;
+    }
+    tree_free(&T[0]); tree_free(&T[1]);
+    free(Q0); free(Q1);
+    return rc;
+}
+
+/* frame pairs that blocked extensions: full-report check of the rejected end points */
+void aa_rx_mp_collisions(struct aa_rx_mp *mp, struct aa_rx_cl_set *set) {
+    if (!mp->cl || mp->n_blocked == 0) return;
+    uint32_t *bits = (uint32_t *)calloc(mp->n_blocked / 32 + 2, sizeof(uint32_t));
+    aa_rx_cl_track_collisions(mp->cl, 1);
+    aa_rx_cl_check_batch(mp->cl, mp->n_blocked, mp->n_sub, mp->ids, mp->n_all, mp->q_start_all, mp->blocked, mp->n_sub, bits);
+    aa_rx_cl_batch_collisions(mp->cl, set);
+    aa_rx_cl_track_collisions(mp->cl, 0);
+    free(bits);
+}

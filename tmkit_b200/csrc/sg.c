@@ -438,6 +438,67 @@ int aa_rx_sg_get_limit_pos(const struct aa_rx_sg *sg, aa_rx_config_id id, double
     return 0;
 }
 
+/* ------------------------------------------------------------------ frame accessors, chains */
+int aa_rx_sg_frame_type(const struct aa_rx_sg *sg, aa_rx_frame_id id) {
+    need_init(sg, "aa_rx_sg_frame_type");
+    if (id < 0 || (size_t)id >= sg->n_f) tmk_die("aa_rx_sg_frame_type: bad frame id %d", id);
+    return sg->type[id];
+}
+aa_rx_config_id aa_rx_sg_frame_config(const struct aa_rx_sg *sg, aa_rx_frame_id id) {
+    need_init(sg, "aa_rx_sg_frame_config");
+    if (id < 0 || (size_t)id >= sg->n_f) tmk_die("aa_rx_sg_frame_config: bad frame id %d", id);
+    return sg->type[id] == TMK_FIXED ? AA_RX_CONFIG_NONE : sg->qidx[id];
+}
+void aa_rx_sg_frame_axis(const struct aa_rx_sg *sg, aa_rx_frame_id id, double axis[3]) {
+    need_init(sg, "aa_rx_sg_frame_axis");
+    if (id < 0 || (size_t)id >= sg->n_f) tmk_die("aa_rx_sg_frame_axis: bad frame id %d", id);
+    memcpy(axis, sg->axis + 3 * (size_t)id, sizeof(double) * 3);
+}
+
+struct aa_rx_sg_sub {
+    const struct aa_rx_sg *sg;
+    aa_rx_frame_id root, tip;
+    size_t n_sub;
+    aa_rx_config_id *ids; /* configuration variables on the chain, root -> tip, each once */
+    size_t n_frames;
+    aa_rx_frame_id *frames; /* frames on the chain, root -> tip (root itself excluded) */
+};
+
+/* reference: tm-blocks.py:202 aa.scene_chain(scene, "", frame) */
+struct aa_rx_sg_sub *aa_rx_sg_chain_create(const struct aa_rx_sg *sg, aa_rx_frame_id root, aa_rx_frame_id tip) {
+    need_init(sg, "aa_rx_sg_chain_create");
+    if (tip < 0 || (size_t)tip >= sg->n_f) tmk_die("aa_rx_sg_chain_create: bad tip frame %d", tip);
+    if (root != AA_RX_FRAME_ROOT && (root < 0 || (size_t)root >= sg->n_f)) tmk_die("aa_rx_sg_chain_create: bad root frame %d", root);
+    struct aa_rx_sg_sub *s = (struct aa_rx_sg_sub *)calloc(1, sizeof(*s));
+    s->sg = sg; s->root = root; s->tip = tip;
+    size_t depth = 0;
+    int f = tip;
+    while (f != root && f >= 0) { depth++; f = sg->parent[f]; }
+    if (f != root) tmk_die("aa_rx_sg_chain_create: frame %d is not an ancestor of frame %d", root, tip);
+    s->frames = (aa_rx_frame_id *)malloc(sizeof(int) * (depth + 1));
+    s->ids = (aa_rx_config_id *)malloc(sizeof(int) * (depth + 1));
+    s->n_frames = depth;
+    f = tip;
+    for (size_t k = depth; k-- > 0;) { s->frames[k] = f; f = sg->parent[f]; }
+    for (size_t k = 0; k < depth; k++) {
+        int fr = s->frames[k];
+        if (sg->type[fr] == TMK_FIXED) continue;
+        int seen = 0;
+        for (size_t j = 0; j < s->n_sub; j++) seen |= s->ids[j] == sg->qidx[fr];
+        if (!seen) s->ids[s->n_sub++] = sg->qidx[fr];
+    }
+    return s;
+}
+void aa_rx_sg_sub_destroy(struct aa_rx_sg_sub *s) {
+    if (!s) return;
+    free(s->frames); free(s->ids); free(s);
+}
+size_t aa_rx_sg_sub_config_count(const struct aa_rx_sg_sub *s) { return s->n_sub; }
+const aa_rx_config_id *aa_rx_sg_sub_configs(const struct aa_rx_sg_sub *s) { return s->ids; }
+aa_rx_frame_id aa_rx_sg_sub_tip(const struct aa_rx_sg_sub *s) { return s->tip; }
+const struct aa_rx_sg *tmk_sub_sg(const struct aa_rx_sg_sub *s) { return s->sg; }
+size_t tmk_sub_frames(const struct aa_rx_sg_sub *s, const aa_rx_frame_id **frames) { *frames = s->frames; return s->n_frames; }
+
 /* ------------------------------------------------------------------ FK entry (device) */
 void aa_rx_sg_tf(const struct aa_rx_sg *sg, size_t n_q, const double *q, size_t n_tf, double *TF_rel, size_t ld_rel,
                  double *TF_abs, size_t ld_abs) {

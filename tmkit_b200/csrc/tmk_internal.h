@@ -12,6 +12,7 @@ extern "C" {
 #endif
 
 enum { TMK_FIXED = 0, TMK_REVOLUTE = 1, TMK_PRISMATIC = 2 };
+#define TMK_MP_MAXSUB 24 /* configuration variables of one motion query (= TMK_MAXSUB of the kernels) */
 enum { TMK_SPHERE = 0, TMK_BOX = 1, TMK_CYLINDER = 2, TMK_MESH = 3 };
 
 struct aa_rx_mesh {
@@ -100,6 +101,11 @@ void tmk_qmul(const double *a, const double *b, double *c);
 void tmk_qrot(const double *q, const double *v, double *out);
 void tmk_tfmul(const double *a, const double *b, double *c);
 void tmk_tfinv(const double *a, double *c);
+
+/* sub-scene-graph internals (sg.c) used by the motion planner (mp.c) */
+struct aa_rx_sg_sub;
+const struct aa_rx_sg *tmk_sub_sg(const struct aa_rx_sg_sub *s);
+size_t tmk_sub_frames(const struct aa_rx_sg_sub *s, const aa_rx_frame_id **frames);
 
 /* implemented in cl.cu */
 void tmk_dev_sg_release(void *dev);
