@@ -211,17 +211,75 @@ def config_dict(workload):
             "l2": f"inputs rotate over a ring of {RING} distinct batches" + (" (> L2)" if kind == "configs" else "")}
 
 
+def run_sussman(args):
+    """BASELINE configs[0]: the motion side of the Baxter Sussman task-motion plan, end to end
+    (tmkit_b200/sussman.py), beside the CPU restatement replaying exactly the same validity work."""
+    import torch
+    from oracle import oracle as O
+    from tmkit_b200 import scenes as S
+    from tmkit_b200 import sussman as SU
+    from tmkit_b200 import workloads as W
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the validity check has no CPU fallback")
+    for w in range(max(1, args.warmup)):
+        SU.run(seed=900 + w)
+    runs = []
+    for k in range(args.steps):
+        log = []
+        r = SU.run(seed=k, edge_log=log)
+        runs.append((r, log))
+    ok = [r for r, _ in runs if r.ok]
+    tot = float(np.median([r.times["total"] for r in ok])) if ok else None
+    # CPU baseline: the oracle (early-out) on the edges of one run, one thread (the reference's planner is
+    # single-threaded) and all cores
+    r, log = next(((r, log) for r, log in runs if r.ok), runs[0])
+    cores = os.cpu_count() or 1
+    cpu = {}
+    n_edges = 0
+    for label, th in (("1", 1), ("all", cores)):
+        t = 0.0
+        for desc, q_start, names, q0e, q1e in log:
+            orc = O.OracleScene(S.flatten(desc))
+            orc.allow_config(q_start)
+            lim = W.arm_limit_table(names)
+            t0 = time.perf_counter()
+            orc.check_edges(orc.config_ids(names), q_start, q0e, q1e, W.seg_len(lim), early_out=True, threads=th)
+            t += time.perf_counter() - t0
+            if label == "1":
+                n_edges += len(q0e)
+        cpu[label] = t
+    split = {k: float(np.median([x.times[k] for x in ok])) for k in ("ik", "rrt", "simplify", "scene")} if ok else {}
+    line = {
+        "metric": "Baxter Sussman motion-plan time (6 motion queries: IK + RRT-Connect + simplify + reparent)",
+        "value": tot, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None if tot is None else tot * 1e3, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "restated Baxter fixture + reference Sussman scene files",
+        "config": {"workload": "BASELINE configs[0]: demo/baxter-sussman, task plan fixed (task planner out of scope), "
+                               "motion timeout 3 s, simplify on", "success": f"{len(ok)}/{len(runs)}"},
+        "split_s": split,
+        "counters": r.counters,
+        "cpu_baseline": {"value": cpu["all"], "unit": "s", "cores": cores, "kind": "port",
+                         "sample": f"oracle replay of the {n_edges} edges one plan checked (validity work only)",
+                         "single_thread_s": cpu["1"]},
+        "validity_s_gpu": split.get("rrt", 0.0) + split.get("simplify", 0.0),
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="configs", choices=["configs", "edges", "blocks", "clutter"])
+    ap.add_argument("--workload", default="configs", choices=["configs", "edges", "blocks", "clutter", "sussman"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    if args.workload == "sussman":
+        run_sussman(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

@@ -252,6 +252,10 @@ struct tmk_mp_stats {
     double ik_s, rrt_s, simplify_s;
 };
 void aa_rx_mp_stats(const struct aa_rx_mp *mp, struct tmk_mp_stats *out);
+/* measurement aid: record the end points (n x n_sub each) of every edge the query checks, so that a
+ * CPU baseline can be timed on exactly the same work */
+void aa_rx_mp_edge_log(struct aa_rx_mp *mp, int enable);
+size_t aa_rx_mp_edge_log_get(const struct aa_rx_mp *mp, const double **q0, const double **q1);
 
 /* Plan files (doc/md/planfile.md:13-76; grammar src/planfile.l:77-192): line-based text,
  * "a ACTION args..", "r frame new_parent", "m config names..", "p values..", "# comment". */

@@ -105,6 +105,8 @@ SIGNATURES = {
     "aa_rx_mp_plan": (_i, [_vp, _d, _vp, _vp]),
     "aa_rx_mp_collisions": (None, [_vp, _vp]),
     "aa_rx_mp_stats": (None, [_vp, _vp]),
+    "aa_rx_mp_edge_log": (None, [_vp, _i]),
+    "aa_rx_mp_edge_log_get": (_sz, [_vp, _vp, _vp]),
     "tmk_plan_create": (_vp, []),
     "tmk_plan_destroy": (None, [_vp]),
     "tmk_plan_add_action": (None, [_vp, _cs]),
@@ -556,6 +558,19 @@ class MotionPlanner:
         s = CollisionSet(self.ssg.sg)
         self.L.aa_rx_mp_collisions(self.h, s.h)
         return s
+
+    def edge_log(self, enable: bool = True):
+        self.L.aa_rx_mp_edge_log(self.h, int(enable))
+
+    def edge_log_get(self):
+        a, b = C.c_void_p(0), C.c_void_p(0)
+        n = self.L.aa_rx_mp_edge_log_get(self.h, C.byref(a), C.byref(b))
+        ns = len(self.ssg.config_ids())
+        if n == 0:
+            return np.zeros((0, ns)), np.zeros((0, ns))
+        q0 = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_double)), shape=(n, ns)).copy()
+        q1 = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_double)), shape=(n, ns)).copy()
+        return q0, q1
 
     def stats(self) -> MpStats:
         st = MpStats()

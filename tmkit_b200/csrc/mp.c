@@ -47,6 +47,9 @@ struct aa_rx_mp {
     size_t n_blocked;
     double *blocked; /* end points of rejected extensions (for the collision feed-back) */
     struct tmk_mp_stats st;
+    int log_on;          /* measurement aid: keep every checked edge so that a CPU baseline can replay them */
+    size_t log_n, log_cap;
+    double *log_q0, *log_q1;
 };
 
 static double now_s(void) {
@@ -125,6 +128,7 @@ void aa_rx_mp_destroy(struct aa_rx_mp *mp) {
     if (!mp) return;
     if (mp->cl) aa_rx_cl_destroy(mp->cl);
     free(mp->lo); free(mp->hi); free(mp->q_start_all); free(mp->blocked);
+    free(mp->log_q0); free(mp->log_q1);
     free(mp);
 }
 
@@ -132,6 +136,11 @@ void aa_rx_mp_set_simplify(struct aa_rx_mp *mp, int simplify) { mp->simplify = s
 void aa_rx_mp_set_track_collisions(struct aa_rx_mp *mp, int track) { mp->track = track; }
 void aa_rx_mp_set_seed(struct aa_rx_mp *mp, uint64_t seed) { mp->rng = seed * 0x9e3779b97f4a7c15ull + 1; }
 void aa_rx_mp_stats(const struct aa_rx_mp *mp, struct tmk_mp_stats *out) { *out = mp->st; }
+void aa_rx_mp_edge_log(struct aa_rx_mp *mp, int enable) { mp->log_on = enable; mp->log_n = 0; }
+size_t aa_rx_mp_edge_log_get(const struct aa_rx_mp *mp, const double **q0, const double **q1) {
+    *q0 = mp->log_q0; *q1 = mp->log_q1;
+    return mp->log_n;
+}
 
 /* start configuration; what collides there is allowed for this query (in-tree
  * analogue demo/tmpexec.c:118) */
@@ -371,6 +380,16 @@ int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
 static size_t check_edges(struct aa_rx_mp *mp, size_t n_edge, const double *Q0, const double *Q1, uint32_t *bits) {
     mp->st.n_edge_calls++;
     mp->st.n_edges_checked += n_edge;
+    if (mp->log_on) {
+        if (mp->log_n + n_edge > mp->log_cap) {
+            mp->log_cap = 2 * (mp->log_n + n_edge) + 1024;
+            mp->log_q0 = (double *)realloc(mp->log_q0, sizeof(double) * mp->log_cap * mp->n_sub);
+            mp->log_q1 = (double *)realloc(mp->log_q1, sizeof(double) * mp->log_cap * mp->n_sub);
+        }
+        memcpy(mp->log_q0 + mp->log_n * mp->n_sub, Q0, sizeof(double) * n_edge * mp->n_sub);
+        memcpy(mp->log_q1 + mp->log_n * mp->n_sub, Q1, sizeof(double) * n_edge * mp->n_sub);
+        mp->log_n += n_edge;
+    }
     return aa_rx_cl_check_edges(mp->cl, n_edge, mp->n_sub, mp->ids, mp->n_all, mp->q_start_all, Q0, Q1, mp->n_sub, mp->seg_len,
                                 bits, NULL);
 }

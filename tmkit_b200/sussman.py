@@ -107,6 +107,8 @@ def run(seed: int = 0, task_plan=TASK_PLAN, timeout: float = MOTION_TIMEOUT, sim
         mp.set_seed(1000 * seed + k)
         mp.set_simplify(simplify)
         mp.set_start(q)
+        if edge_log is not None:
+            mp.edge_log(True)
         res.times["scene"] += time.perf_counter() - t0
         n_goal = mp.set_wsgoal(goal)
         path = mp.plan(timeout) if n_goal else None
@@ -118,6 +120,8 @@ def run(seed: int = 0, task_plan=TASK_PLAN, timeout: float = MOTION_TIMEOUT, sim
         res.queries.append({"action": " ".join(str(a) for a in act), "goals": int(st.n_goals), "ik_s": st.ik_s, "rrt_s": st.rrt_s,
                             "simplify_s": st.simplify_s, "iterations": int(st.n_iterations),
                             "edges": int(st.n_edges_checked), "waypoints": 0 if path is None else len(path)})
+        if edge_log is not None:
+            edge_log.append((copy.deepcopy(sc), q.copy(), ssg.config_names(), *mp.edge_log_get()))
         if path is None and name == "PUT-DOWN" and attempt + 1 < len(PUT_DOWN_CELLS):
             i, j = PUT_DOWN_CELLS[attempt + 1]
             todo.insert(0, ((name, obj, dst, i, j), attempt + 1))
