@@ -733,7 +733,8 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
     if (!(seg_len > 0)) tmk_die("edges: seg_len must be positive");
     if (n_edge > 0x7ffffff0u) tmk_die("edges: more than 2^31 edges in one call");
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
-    if (cl->use_tile && im.wcfg_e.smem > 0 && !st ) {
+    const size_t small = getenv("TMK_EDGE_SMALL") ? (size_t)atol(getenv("TMK_EDGE_SMALL")) : 0; /* tuning aid */
+    if (cl->use_tile && im.wcfg_e.smem > 0 && !st && n_edge >= small) {
         /* fast path: bisection levels through the warp pipelines (pipeline.cuh) */
         UncList u = unc_list(cl, n_edge * 4, s);
         if (n_edge == 0) return;
