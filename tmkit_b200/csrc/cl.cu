@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "kernels.cuh"
@@ -518,6 +519,49 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     /* candidate pairs: every (moving, other) pair that is not same-frame / allowed.  A pair of two
      * moving geometries is owned by the later one (its partner's pose already exists when the
      * kernel reaches it).  Grouped by owner, then by narrowphase class. */
+    /* reach of every moving geometry: it stays inside the ball (centre, reach) whatever the varied
+     * joints do (centre = origin of the chain's first varied joint; every further joint origin adds its
+     * offset, prismatic joints their travel).  Static partners outside that ball can never be touched and
+     * are dropped from the list - verdicts are unaffected. */
+    std::vector<double> j_cx(joints.size() * 3, 0.0), j_reach(joints.size(), 0.0);
+    for (size_t k = 0; k < joints.size(); k++) {
+        const DJoint<double> &J = joints[k];
+        double travel = 0;
+        if (J.type == TMK_PRISMATIC) {
+            int cid = sub_ids[J.qslot];
+            double lo = sg->lim_min[cid], hi = sg->lim_max[cid];
+            double an = sqrt(J.ax[0] * J.ax[0] + J.ax[1] * J.ax[1] + J.ax[2] * J.ax[2]);
+            travel = (std::isnan(lo) || std::isnan(hi)) ? INFINITY : an * std::max(fabs(lo + J.off), fabs(hi + J.off));
+        }
+        if (J.parent < 0) {
+            for (int c = 0; c < 3; c++) j_cx[3 * k + c] = J.E[4 + c];
+            j_reach[k] = travel;
+        } else {
+            for (int c = 0; c < 3; c++) j_cx[3 * k + c] = j_cx[3 * J.parent + c];
+            j_reach[k] = j_reach[J.parent] + sqrt(J.E[4] * J.E[4] + J.E[5] * J.E[5] + J.E[6] * J.E[6]) + travel;
+        }
+    }
+    auto unreachable = [&](const DGeom<double> &A, const DGeom<double> &B) {
+        const double *c = &j_cx[3 * A.slot];
+        double reach = j_reach[A.slot] + sqrt(A.tf[4] * A.tf[4] + A.tf[5] * A.tf[5] + A.tf[6] * A.tf[6]) + A.brad;
+        if (A.shape == TMK_MESH) reach += sqrt(A.dim[0] * A.dim[0] + A.dim[1] * A.dim[1] + A.dim[2] * A.dim[2]);
+        if (!(reach < 1e9)) return false;
+        double d[3] = {c[0] - B.tf[4], c[1] - B.tf[5], c[2] - B.tf[6]}, dist;
+        if (B.shape == TMK_BOX) {
+            double qi[4] = {-B.tf[0], -B.tf[1], -B.tf[2], B.tf[3]}, l[3];
+            tmk_qrot(qi, d, l);
+            double e2 = 0;
+            for (int k = 0; k < 3; k++) { double e = fabs(l[k]) - B.dim[k]; if (e > 0) e2 += e * e; }
+            dist = sqrt(e2);
+        } else {
+            double off = 0;
+            if (B.shape == TMK_MESH) off = sqrt(B.dim[0] * B.dim[0] + B.dim[1] * B.dim[1] + B.dim[2] * B.dim[2]);
+            dist = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) - B.brad - off;
+        }
+        return dist > reach * (1 + 1e-9) + 1e-4;
+    };
+    size_t n_unreachable = 0;
+
     struct P { uint32_t w; int fa, fb, owner, seg; };
     std::vector<P> pairs;
     for (size_t a = 0; a < cl->n_g; a++) {
@@ -527,6 +571,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
             if (g2m[b] >= 0 && g2m[b] > g2m[a]) continue; /* owned by b */
             int fa = cl->geoms[a].frame, fb = cl->geoms[b].frame;
             if (!pair_live(cl, fa, fb)) continue;
+            if (g2m[b] < 0 && unreachable(mg[g2m[a]], sgv[g2s[b]])) { n_unreachable++; continue; }
             int cls = pair_class(cl->geoms[a].shape, cl->geoms[b].shape);
             P p;
             p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls, cl->geoms[b].shape)

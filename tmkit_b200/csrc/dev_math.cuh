@@ -598,6 +598,70 @@ TMK_HD int quick_pair(int ka_in, const QG &A_in, int kb_in, const QG &B_in) {
         if (g > eps) return SEP;
         if (fabsf(t0) < A.h0 - eps && fabsf(t1) < A.h1 - eps && fabsf(t2) < A.h2 - eps) return HIT; /* cyl centre in box */
         if (fabsf(tz) < B.h1 - eps && rho < B.h0 - eps) return HIT;                                   /* box centre in cyl */
+        {
+            /* the cylinder's axis segment passes through the box shrunk by eps (the usual way an arm link
+             * meets a table slab: its centre is outside, its axis crosses) - slab clipping in A's frame */
+            const float tt[3] = {t0, t1, t2};
+            const float uu[3] = {dot(B.z, A.x), dot(B.z, A.y), dot(B.z, A.z)};
+            const float gg[3] = {A.h0 - eps, A.h1 - eps, A.h2 - eps};
+            float lo = -(B.h1 - eps), hi = B.h1 - eps;
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (gg[i] <= 0.f) ok = false;
+                if (fabsf(uu[i]) < 1e-6f) {
+                    if (fabsf(tt[i]) >= gg[i]) ok = false;
+                } else {
+                    const float inv = 1.0f / uu[i];
+                    const float sa = (-gg[i] - tt[i]) * inv, sb = (gg[i] - tt[i]) * inv;
+                    lo = fmaxf(lo, fminf(sa, sb));
+                    hi = fminf(hi, fmaxf(sa, sb));
+                }
+            }
+            if (ok && lo < hi) return HIT;
+            /* the cylinder's extreme point towards each face plane of the box (support point of the
+             * cylinder shrunk by eps) lies inside the shrunk box: a rim dipping into a slab */
+            if (ok) {
+                const float rr = B.h0 - eps, hh = B.h1 - eps;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const float sg = tt[i] > 0.f ? -1.0f : 1.0f; /* n = sg * e_i */
+                    const float nu = sg * uu[i];
+                    const float pl2 = 1.0f - uu[i] * uu[i];
+                    const float ax = nu >= 0.f ? hh : -hh;
+                    float q[3] = {tt[0] + uu[0] * ax, tt[1] + uu[1] * ax, tt[2] + uu[2] * ax};
+                    if (pl2 > 1e-6f) {
+                        const float k = rr / sqrtf(pl2);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) q[c] += k * (sg * ((c == i ? 1.0f : 0.0f) - uu[i] * uu[c]));
+                    }
+                    if (fabsf(q[0]) < gg[0] && fabsf(q[1]) < gg[1] && fabsf(q[2]) < gg[2]) return HIT;
+                    /* thin slabs: the extreme point overshoots to the far side.  From a point P of the axis
+                     * segment walk radially (perpendicular to the axis, towards the box's mid-plane x_i = 0)
+                     * until that plane; if it is reached within the radius the landing point belongs to the
+                     * cylinder, and it is inside the box if its other two coordinates are. */
+                    if (pl2 > 1e-6f) {
+                        const float ipl = 1.0f / pl2;
+#pragma unroll
+                        for (int c3 = 0; c3 < 3; c3++) {
+                            const float sa = c3 == 0 ? 0.f : (c3 == 1 ? hh : -hh);
+                            const float P[3] = {tt[0] + uu[0] * sa, tt[1] + uu[1] * sa, tt[2] + uu[2] * sa};
+                            if (P[i] * P[i] * ipl < rr * rr) { /* radial distance to the plane < radius */
+                                const float f = -P[i] * ipl;    /* q = P + f * (e_i - u_i u) */
+                                bool in = true;
+#pragma unroll
+                                for (int c = 0; c < 3; c++) {
+                                    if (c == i) continue;
+                                    const float qc = P[c] - f * uu[i] * uu[c];
+                                    in = in && fabsf(qc) < gg[c];
+                                }
+                                if (in) return HIT;
+                            }
+                        }
+                    }
+                }
+            }
+        }
         return NEED;
     }
     /* cylinder - cylinder */

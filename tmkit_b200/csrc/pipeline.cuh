@@ -332,6 +332,20 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                     int p = PA[3 * a];
                     const int e0 = PA[3 * a + 1], e1 = PA[3 * a + 2], e2 = PA[3 * a + 3];
                     /* static partners by bounding sphere */
+                    for (; p + 4 <= e0; p += 4) { /* four tests, one vote: most groups have no survivor */
+                        bool pass[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float4 c4 = PS4[p + u];
+                            const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+                            const float reach = ra + c4.w;
+                            pass[u] = live && dx * dx + dy * dy + dz * dz <= reach * reach;
+                        }
+                        if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) enqueue(p + u, pass[u]);
+                        }
+                    }
                     for (; p < e0; p++) {
                         const float4 c4 = PS4[p];
                         const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
