@@ -86,7 +86,14 @@ class ClockSampler:
                 self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.005 if self.nvml else 0.1)
+            self._stop.wait(0.002 if self.nvml else 0.1)
+
+    def sample_now(self):
+        """one sample from the calling thread (the timed loop is short and keeps the interpreter busy)"""
+        try:
+            self._sample_nvml() if self.nvml else self._sample_smi()
+        except Exception:
+            pass
 
     def start(self):
         self.t.start()
@@ -187,8 +194,8 @@ def run_reference(args):
         vals.append(v)
     v = float(np.median(vals))
     line = {
-        "impl": "reference", "metric": metric_name(args.workload), "value": v, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "impl": "reference", "sample_units": n, "sample_s": dt, "metric": metric_name(args.workload), "value": v, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args.workload),
         "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
@@ -269,7 +276,7 @@ def run_sussman(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="configs", choices=["configs", "edges", "blocks", "clutter", "sussman"])
@@ -363,6 +370,8 @@ def main():
         ev[0].record(ts)
         for i in range(args.steps):
             step(args.warmup + i)
+            if rank == 0 and i % 16 == 8:
+                sampler.sample_now()  # while the GPU is busy with the steps already queued
         ev[1].record(ts)
         barrier()
         ms_total = ev[0].elapsed_time(ev[1])

@@ -309,6 +309,25 @@ def test_kernel_variants_agree(gpu_sussman, monkeypatch):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("env", [{"TMK_QCAP": "4"}, {"TMK_QCAP": "4", "TMK_UNC_CAP": "64"}, {"TMK_UNC_CAP": "1"}])
+def test_overflow_paths_keep_verdicts(gpu_sussman, monkeypatch, env):
+    """full shared-memory queues hand their pairs to the exact (double) re-check, and a full undecided
+    list triggers the brute-force double kernel: slower, same bits - configurations and edges."""
+    sc, orc, sg, cl, q0 = gpu_sussman
+    sub = sg.config_indices(S.RIGHT_ARM)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    Q = W.random_configs(lim, 6000, seed=41)
+    a, b = W.random_edges(lim, 700, seed=41)
+    want = cl.check_batch(sub, q0, Q)
+    ewant, efirst = cl.check_edges(sub, q0, a, b, W.seg_len(lim))
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cl2 = A.Collision(sg)
+    assert np.array_equal(cl2.check_batch(sub, q0, Q), want)
+    ev, first = cl2.check_edges(sub, q0, a, b, W.seg_len(lim))
+    assert np.array_equal(ev, ewant) and np.array_equal(first, efirst)
+
+
 def test_track_collisions_feedback(gpu_sussman):
     """:track-collisions (lisp/python/tmsmtpy.lisp:59): OR of the colliding frame pairs of a batch."""
     sc, orc, sg, cl, q0 = gpu_sussman

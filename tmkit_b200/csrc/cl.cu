@@ -694,6 +694,7 @@ static void stats_begin(struct aa_rx_cl *cl) {
 static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     UncList u;
     u.cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states / 2), 0x7fffffffu);
+    if (const char *e = getenv("TMK_UNC_CAP")) u.cap = (uint32_t)std::max(1, atoi(e)); /* test aid: forces k_overflow_all */
     cl->d_unc.need(sizeof(uint4) * (size_t)u.cap);
     cl->d_cnt.need(128);
     CK(cudaMemsetAsync(cl->d_cnt.p, 0, 128, s));

@@ -634,6 +634,10 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
     cfg.q3_cap = (left * 5 / 16) / 4 / nw;
     cfg.q1_cap = (left - 4 * cfg.q2_cap - 4 * cfg.q3_cap * nw) / 4 / nw;
     if (cfg.q1_cap > (1 << 16)) cfg.q1_cap = 1 << 16;
+    if (const char *e = getenv("TMK_QCAP")) { /* test aid: tiny queues exercise the overflow -> exact re-check path */
+        int c = atoi(e);
+        if (c > 0) { cfg.q1_cap = std::min(cfg.q1_cap, c); cfg.q2_cap = std::min(cfg.q2_cap, c); cfg.q3_cap = std::min(cfg.q3_cap, c); }
+    }
     cfg.off_q1 = off; off += cfg.q1_cap * nw * 4;
     cfg.off_q2 = off; off += cfg.q2_cap * 4;
     cfg.off_q3 = off; off += cfg.q3_cap * nw * 4;
