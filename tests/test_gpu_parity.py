@@ -309,10 +309,12 @@ def test_kernel_variants_agree(gpu_sussman, monkeypatch):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("env", [{"TMK_QCAP": "4"}, {"TMK_QCAP": "4", "TMK_UNC_CAP": "64"}, {"TMK_UNC_CAP": "1"}])
+@pytest.mark.parametrize("env", [{"TMK_QCAP": "4"}, {"TMK_QCAP": "4", "TMK_SPILL_CAP": "0"},
+                                 {"TMK_QCAP": "4", "TMK_SPILL_CAP": "16", "TMK_UNC_CAP": "64"}, {"TMK_UNC_CAP": "1"}])
 def test_overflow_paths_keep_verdicts(gpu_sussman, monkeypatch, env):
-    """full shared-memory queues hand their pairs to the exact (double) re-check, and a full undecided
-    list triggers the brute-force double kernel: slower, same bits - configurations and edges."""
+    """full shared-memory queues spill into global memory, a full spill area hands pairs to the exact
+    (double) re-check, and a full undecided list triggers the brute-force double kernel: slower, same
+    bits - configurations and edges."""
     sc, orc, sg, cl, q0 = gpu_sussman
     sub = sg.config_indices(S.RIGHT_ARM)
     lim = W.arm_limit_table(S.RIGHT_ARM)
@@ -463,6 +465,33 @@ def test_dual_arm_clutter_scene(n_prims):
     ev, first = cl.check_edges(sub, q0, a, b, W.seg_len(lim))
     est, _, ofirst, _ = orc.check_edges(orc.config_ids(names), q0, a, b, W.seg_len(lim), threads=CORES)
     _assert_verdicts(ev, est, "dual-arm clutter edges", max_band_frac=0.05)
+
+
+def test_static_grid_equals_brute_force(monkeypatch):
+    """large scenes put their small static geometry into a uniform grid; the pair-list sweep (grid off)
+    must give the same bits - configurations and edges, obstacles of every size class."""
+    sc = S.clutter_scene(300, seed=5)
+    # a few big obstacles that stay in the brute-force list, one of them spanning many cells
+    sc.add(S.Frame("wall", "", S.FIXED, S.quat_from_rpy(0.2, 0.1, 0.7), (0.9, 0.0, 0.4), geoms=[S.Geom(S.BOX, (0.05, 2.0, 1.5))]))
+    sc.add(S.Frame("ball", "", S.FIXED, (0, 0, 0, 1), (0.2, 0.9, 0.9), geoms=[S.Geom(S.SPHERE, (0.35, 0, 0))]))
+    q0 = S.q0_vector(sc)
+    names = S.RIGHT_ARM + S.LEFT_ARM
+    lim = W.arm_limit_table(names)
+    Q = W.random_configs(lim, 20000, seed=6)
+    a, b = W.random_edges(lim, 1500, seed=7)
+    sg, cl, _ = _gpu_scene(sc, q0)
+    sub = sg.config_indices(names)
+    v_grid = cl.check_batch(sub, q0, Q)
+    e_grid, f_grid = cl.check_edges(sub, q0, a, b, W.seg_len(lim))
+    monkeypatch.setenv("TMK_NO_GRID", "1")
+    cl2 = A.Collision(sg)
+    assert np.array_equal(cl2.check_batch(sub, q0, Q), v_grid)
+    e2, f2 = cl2.check_edges(sub, q0, a, b, W.seg_len(lim))
+    assert np.array_equal(e2, e_grid) and np.array_equal(f2, f_grid)
+    assert 0.005 < v_grid.mean() < 0.9
+    orc = _oracle_scene(sc, q0)
+    st, _ = orc.check_batch(orc.config_ids(names), q0, Q[:1500], threads=CORES, early_out=True)
+    _assert_verdicts(v_grid[:1500], st, "clutter with a grid")
 
 
 def test_prismatic_and_sphere_scene():

@@ -174,7 +174,7 @@ static void mesh_compile(const struct aa_rx_mesh *m, HostMesh &hm) {
 
 /* ------------------------------------------------------------------ the collision context */
 struct ImageDev {
-    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4;
+    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, g_cells, g_items, g_live;
     Image<float> f;
     Image<double> d;
     std::vector<uint32_t> h_pairs;
@@ -208,6 +208,7 @@ struct aa_rx_cl {
     ImageDev img;
 
     /* batch scratch */
+    DBuf d_spill;
     DBuf d_q, d_q1, d_bits, d_unc, d_cnt, d_first, d_pairhit, d_stats, d_nd, d_alive0, d_alive1, d_efirst;
     uint32_t *h_cnt; /* pinned */
     int track, stats_on;
@@ -327,9 +328,10 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     if (!cl) return;
     cudaStreamSynchronize(cl->stream);
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
-                    &cl->d_gout, &cl->d_tf, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
+                    &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
-                    &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4};
+                    &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4, &cl->img.tpairs, &cl->img.g_cells, &cl->img.g_items,
+                    &cl->img.g_live};
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     cudaFreeHost(cl->h_cnt);
@@ -586,12 +588,69 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         if (x.seg != y.seg) return x.seg < y.seg;
         return (x.w >> 28) < (y.w >> 28);
     });
-    std::vector<int> pa_begin(3 * mg.size() + 1, 0);
-    for (auto &p : pairs) pa_begin[3 * p.owner + p.seg + 1]++;
-    for (size_t k = 0; k < 3 * mg.size(); k++) pa_begin[k + 1] += pa_begin[k];
     im.h_pairs.clear(); im.pair_fa.clear(); im.pair_fb.clear();
     for (auto &p : pairs) { im.h_pairs.push_back(p.w); im.pair_fa.push_back(p.fa); im.pair_fb.push_back(p.fb); }
     if (im.h_pairs.size() >= (1u << 27)) tmk_die("batch: too many candidate pairs");
+
+    /* large scenes: small static geometry goes into a uniform grid and leaves the pipeline's pair list */
+    const double GRID_RMAX = 0.25, GRID_H = 0.4;
+    std::vector<uint8_t> gridded(sgv.size(), 0);
+    size_t n_gridded = 0;
+    for (size_t b = 0; b < sgv.size(); b++)
+        if (sgv[b].shape != TMK_MESH && sgv[b].brad <= GRID_RMAX) { gridded[b] = 1; n_gridded++; }
+    const bool grid_on = n_gridded >= 96 && !getenv("TMK_NO_GRID");
+    if (!grid_on) std::fill(gridded.begin(), gridded.end(), 0);
+    StaticGrid grid;
+    memset(&grid, 0, sizeof(grid));
+    std::vector<int> cell_start(2, 0);
+    std::vector<unsigned short> cell_items(1, 0);
+    const int wps = (int)(sgv.size() + 31) / 32;
+    std::vector<uint32_t> live_ms((size_t)std::max<size_t>(1, mg.size() * (size_t)wps), 0u);
+    if (grid_on) {
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (size_t b = 0; b < sgv.size(); b++)
+            if (gridded[b])
+                for (int c = 0; c < 3; c++) { lo[c] = std::min(lo[c], sgv[b].tf[4 + c]); hi[c] = std::max(hi[c], sgv[b].tf[4 + c]); }
+        int dims[3];
+        for (int c = 0; c < 3; c++) dims[c] = std::max(1, std::min(64, (int)floor((hi[c] - lo[c]) / GRID_H) + 1));
+        grid.on = 1;
+        grid.nx = dims[0]; grid.ny = dims[1]; grid.nz = dims[2];
+        grid.ox = (float)lo[0]; grid.oy = (float)lo[1]; grid.oz = (float)lo[2];
+        grid.inv_h = (float)(1.0 / GRID_H);
+        grid.r_max = (float)(GRID_RMAX * (1 + 1e-6) + 1e-5); /* + slack for the float cell arithmetic */
+        grid.wps = wps;
+        auto cell_of = [&](const DGeom<double> &G) {
+            /* the same float arithmetic as the kernel's query (clamped), so that a geometry is always inside
+             * the cell range computed for a query sphere that reaches its centre */
+            int ix[3];
+            const float o[3] = {grid.ox, grid.oy, grid.oz};
+            for (int c = 0; c < 3; c++) {
+                int v = (int)floorf(((float)G.tf[4 + c] - o[c]) * grid.inv_h);
+                ix[c] = std::max(0, std::min(dims[c] - 1, v));
+            }
+            return (ix[2] * dims[1] + ix[1]) * dims[0] + ix[0];
+        };
+        const size_t n_cell = (size_t)dims[0] * dims[1] * dims[2];
+        cell_start.assign(n_cell + 1, 0);
+        for (size_t b = 0; b < sgv.size(); b++)
+            if (gridded[b]) cell_start[cell_of(sgv[b]) + 1]++;
+        for (size_t k = 0; k < n_cell; k++) cell_start[k + 1] += cell_start[k];
+        cell_items.assign(n_gridded + 1, 0);
+        std::vector<int> fill(cell_start.begin(), cell_start.end() - 1);
+        for (size_t b = 0; b < sgv.size(); b++)
+            if (gridded[b]) cell_items[fill[cell_of(sgv[b])]++] = (unsigned short)b;
+        for (auto &p : pairs)
+            if (((p.w >> 24) & 1) && gridded[(p.w >> 8) & 0xffff])
+                live_ms[(size_t)p.owner * wps + (((p.w >> 8) & 0xffff) >> 5)] |= 1u << (((p.w >> 8) & 0xffff) & 31);
+    }
+    std::vector<P> tpairs;
+    for (auto &p : pairs)
+        if (!(((p.w >> 24) & 1) && gridded[(p.w >> 8) & 0xffff])) tpairs.push_back(p);
+    std::vector<uint32_t> h_tpairs;
+    for (auto &p : tpairs) h_tpairs.push_back(p.w);
+    std::vector<int> pa_begin(3 * mg.size() + 1, 0);
+    for (auto &p : tpairs) pa_begin[3 * p.owner + p.seg + 1]++;
+    for (size_t k = 0; k < 3 * mg.size(); k++) pa_begin[k + 1] += pa_begin[k];
 
     /* world-frame quick tables of the static geometry */
     std::vector<SQuick> sq(sgv.size());
@@ -647,10 +706,14 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     upload(im.sq, sq, cl->stream);
     upload(im.jg, jg_begin, cl->stream);
     upload(im.pa, pa_begin, cl->stream);
+    upload(im.tpairs, h_tpairs, cl->stream);
+    upload(im.g_cells, cell_start, cl->stream);
+    upload(im.g_items, cell_items, cl->stream);
+    upload(im.g_live, live_ms, cl->stream);
     {
-        std::vector<float4> ps4(pairs.size() + 1);
-        for (size_t k = 0; k < pairs.size(); k++) {
-            uint32_t w = pairs[k].w;
+        std::vector<float4> ps4(tpairs.size() + 1);
+        for (size_t k = 0; k < tpairs.size(); k++) {
+            uint32_t w = tpairs[k].w;
             if ((w >> 24) & 1) {
                 const SQuick &Q = sq[(w >> 8) & 0xffff];
                 ps4[k] = make_float4(Q.cx, Q.cy, Q.cz, Q.brad);
@@ -675,10 +738,24 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     im.d.jg_begin = im.f.jg_begin = (const int *)im.jg.p;
     im.d.pa_begin = im.f.pa_begin = (const int *)im.pa.p;
     im.d.ps4 = im.f.ps4 = im.ps4.p;
-    tile_configure(im.wcfg, im.f, n_jslab, k_states_tile<SrcConfigs, SinkBits, 256>, k_states_tile<SrcConfigs, SinkBits, 128>);
-    tile_configure(im.wcfg_e, im.f, n_jslab, k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256>,
-                   k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128>);
-    if (im.h_pairs.size() >= (1u << 20)) im.wcfg.smem = im.wcfg_e.smem = -1; /* queue items hold 20-bit pair indices */
+    im.d.t_pairs = im.f.t_pairs = (const uint32_t *)im.tpairs.p;
+    im.d.n_tpair = im.f.n_tpair = (int)h_tpairs.size();
+    grid.cell_start = (const int *)im.g_cells.p;
+    grid.items = (const unsigned short *)im.g_items.p;
+    grid.live = (const uint32_t *)im.g_live.p;
+    im.d.grid = im.f.grid = grid;
+    if (grid.on) {
+        tile_configure(im.wcfg, im.f, n_jslab, k_states_tile<SrcConfigs, SinkBits, 256, true>,
+                       k_states_tile<SrcConfigs, SinkBits, 128, true>);
+        tile_configure(im.wcfg_e, im.f, n_jslab, k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256, true>,
+                       k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128, true>);
+    } else {
+        tile_configure(im.wcfg, im.f, n_jslab, k_states_tile<SrcConfigs, SinkBits, 256, false>,
+                       k_states_tile<SrcConfigs, SinkBits, 128, false>);
+        tile_configure(im.wcfg_e, im.f, n_jslab, k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256, false>,
+                       k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128, false>);
+    }
+    if (mg.size() > 64) im.wcfg.smem = im.wcfg_e.smem = -1; /* queue items hold a 6-bit moving-geometry index */
     im.valid = true;
 }
 
@@ -688,6 +765,19 @@ static void stats_begin(struct aa_rx_cl *cl) {
     if (cl->stats_on) {
         cl->d_stats.need(sizeof(DevStats));
         CK(cudaMemsetAsync(cl->d_stats.p, 0, sizeof(DevStats), cl->stream));
+    }
+}
+
+/* the four instantiations of the pipeline kernel: tile size x static grid */
+template <class Src, class Sink>
+static void launch_tile(const Image<float> &f, const TileCfg &cfg, const Src &src, const Sink &sink, const UncList &u,
+                        unsigned long long *n_states, unsigned grid, cudaStream_t s) {
+    if (cfg.tile == 256) {
+        if (f.grid.on) k_states_tile<Src, Sink, 256, true><<<grid, 256, cfg.smem, s>>>(f, cfg, src, sink, u, n_states);
+        else k_states_tile<Src, Sink, 256, false><<<grid, 256, cfg.smem, s>>>(f, cfg, src, sink, u, n_states);
+    } else {
+        if (f.grid.on) k_states_tile<Src, Sink, 128, true><<<grid, 128, cfg.smem, s>>>(f, cfg, src, sink, u, n_states);
+        else k_states_tile<Src, Sink, 128, false><<<grid, 128, cfg.smem, s>>>(f, cfg, src, sink, u, n_states);
     }
 }
 
@@ -701,6 +791,12 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     u.items = (uint4 *)cl->d_unc.p;
     u.n = (uint32_t *)cl->d_cnt.p;
     u.overflow = (uint32_t *)cl->d_cnt.p + 1;
+    /* per-CTA spill area of the broadphase queue (only touched when a shared-memory region fills up) */
+    u.spill_cap = 1u << 15;
+    if (const char *e = getenv("TMK_SPILL_CAP")) u.spill_cap = (uint32_t)std::max(0, atoi(e)); /* test aid */
+    const size_t ctas = (size_t)std::max(std::max(cl->img.wcfg.grid, cl->img.wcfg_e.grid), 1);
+    cl->d_spill.need(sizeof(uint32_t) * ctas * (size_t)std::max<uint32_t>(u.spill_cap, 1));
+    u.spill = (uint32_t *)cl->d_spill.p;
     return u;
 }
 
@@ -732,12 +828,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         const int T = im.wcfg.tile;
         unsigned grid = (unsigned)std::min<size_t>((src.n + T - 1) / T, (size_t)im.wcfg.grid);
         cudaEvent_t *ev = chunk_begin == 0 ? (cl->cur_ev = timing_begin(cl, s)) : cl->cur_ev;
-        if (T == 256)
-            k_states_tile<SrcConfigs, SinkBits, 256><<<grid, 256, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
-                                                                                      (unsigned long long *)nullptr);
-        else
-            k_states_tile<SrcConfigs, SinkBits, 128><<<grid, 128, im.wcfg.smem, s>>>(im.f, im.wcfg, src, sink, u,
-                                                                                      (unsigned long long *)nullptr);
+        launch_tile<SrcConfigs, SinkBits>(im.f, im.wcfg, src, sink, u, (unsigned long long *)nullptr, grid, s);
         CK(cudaGetLastError());
         cl->stats.n_launches += 1;
         if (c_end < n_cfg) return;
@@ -805,12 +896,8 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         size_t launches = 1;
         for (int L = 0; L < TMK_EDGE_LEVELS; L++) {
             src.alive = cur_alive; src.n_alive = cur_n; src.level = L;
-            if (im.wcfg_e.tile == 256)
-                k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256><<<im.wcfg_e.grid, 256, im.wcfg_e.smem, s>>>(
-                    im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2));
-            else
-                k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128><<<im.wcfg_e.grid, 128, im.wcfg_e.smem, s>>>(
-                    im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2));
+            launch_tile<SrcEdgeLevel, SinkEdgeFirst>(im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2),
+                                                     (unsigned)im.wcfg_e.grid, s);
             CK(cudaGetLastError());
             launches++;
             if (L + 1 < TMK_EDGE_LEVELS) {

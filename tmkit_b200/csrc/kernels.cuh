@@ -45,6 +45,19 @@ __host__ __device__ inline uint32_t pair_pack(int a, int b, int b_static, int cl
 }
 enum { PC_CLOSED = 0, PC_SAT = 1, PC_GJK = 2, PC_MESH = 3 };
 
+/* Uniform grid over the small static geometry of large scenes (hundreds of obstacles): every gridded
+ * geometry sits in the one cell that contains its bounding centre, a query covers the cells within
+ * (radius of the moving geometry + r_max) of its centre. */
+struct StaticGrid {
+    int on;
+    int nx, ny, nz;
+    float ox, oy, oz, inv_h, r_max;
+    const int *cell_start;         /* [nx*ny*nz + 1] */
+    const unsigned short *items;   /* static geometry indices, cell by cell */
+    const uint32_t *live;          /* [n_mg][wps] bit b: pair (a, static b) is a candidate (not allowed-away, reachable) */
+    int wps;
+};
+
 template <typename T> struct Image {
     const DJoint<T> *joints;
     const DGeom<T> *mg;
@@ -55,7 +68,10 @@ template <typename T> struct Image {
     const int *jg_begin; /* [n_joint+1]: moving geometries of joint j are mg[jg_begin[j] .. jg_begin[j+1]) */
     const int *pa_begin; /* [3*n_mg+1]: pairs owned by moving geometry a, in three segments - static partners
                           * tested by bounding sphere [3a], static boxes [3a+1], moving partners [3a+2] .. [3a+3] */
-    const void *ps4;     /* float4[n_pair]: bounding centre + radius of the static partner, in pair order */
+    const void *ps4;     /* float4[n_tpair]: bounding centre + radius of the static partner, in t_pairs order */
+    const uint32_t *t_pairs; /* the pipeline's pair list: `pairs` minus the pairs the grid covers (same array without a grid) */
+    int n_tpair;
+    StaticGrid grid;
     int n_joint, n_mg, n_sg, n_pair;
     int n_sub;
     int static_hit; /* a non-allowed static-static pair collides: every configuration is invalid */

@@ -69,11 +69,24 @@ __device__ __forceinline__ QG qg_from_static(const SQuick &s) {
     return g;
 }
 
+/* queue item: bits 23-30 thread of the tile | 17-22 moving geometry a | 16 partner is static | 0-15 partner b.
+ * The low 23 bits ("pair key") also identify the pair in the undecided list. */
+__device__ __forceinline__ uint32_t item_pack(int tid, int a, int b, int b_static) {
+    return ((uint32_t)tid << 23) | ((uint32_t)a << 17) | ((uint32_t)b_static << 16) | (uint32_t)b;
+}
+#define ITEM_T(e) ((int)((e) >> 23))
+#define ITEM_A(e) ((int)(((e) >> 17) & 63))
+#define ITEM_STATIC(e) ((int)(((e) >> 16) & 1))
+#define ITEM_B(e) ((int)((e)&0xffff))
+#define ITEM_KEY(e) ((e)&0x7fffffu)
+
 struct UncList {
-    uint4 *items;       /* x,y = state identity (Src::unc_id), z = pair, w = mesh triangle or TMK_WHOLE_PAIR */
+    uint4 *items;       /* x,y = state identity (Src::unc_id), z = pair key (ITEM_KEY), w = mesh triangle or TMK_WHOLE_PAIR */
     uint32_t *n;        /* appended count (may exceed cap) */
     uint32_t cap;
     uint32_t *overflow; /* set when an item was dropped: the brute-force double kernel then runs */
+    uint32_t *spill;    /* per-CTA overflow area of the broadphase queue in global memory: [gridDim.x][spill_cap] */
+    uint32_t spill_cap;
 };
 #define TMK_WHOLE_PAIR 0xffffffffu
 __device__ __forceinline__ void unc_emit(const UncList &u, uint32_t id_x, uint32_t id_y, uint32_t pair, uint32_t tri) {
@@ -89,6 +102,18 @@ struct TriEmit {
     uint32_t id_x, id_y, pair;
     __device__ __forceinline__ void operator()(int tri) const { unc_emit(u, id_x, id_y, pair, (uint32_t)tri); }
 };
+
+/* the rare path of the broadphase queues, out of line so that the hot loops stay small: a full
+ * shared-memory region spills into the CTA's global area (same float phases later); only when that is
+ * full too - or for a mesh item - is the pair handed to the exact re-check */
+__device__ __noinline__ void queue_overflow(const UncList unc, uint32_t *spill_n, uint32_t *spill, const uint32_t *unc_x,
+                                            const uint32_t *unc_y, uint32_t item, bool mesh) {
+    if (!mesh) {
+        const uint32_t k = atomicAdd(spill_n, 1u);
+        if (k < unc.spill_cap) { spill[k] = item; return; }
+    }
+    unc_emit(unc, unc_x[ITEM_T(item)], unc_y[ITEM_T(item)], ITEM_KEY(item), TMK_WHOLE_PAIR);
+}
 
 /* ------------------------------------------------------------------ sources of states, sinks of verdicts
  * Src:  count(), prepare(s) -> State (with .live), load1<T>(State, k) = k-th joint value,
@@ -183,14 +208,14 @@ struct SinkEdgeFirst {
  * TILE threads = TILE states per CTA pass; phases are CTA-synchronous so that all warps of an SM
  * execute the same (small) code region at a time - the instruction caches (L0 6 KB, L1.5 32 KB)
  * are the scarce resource of this branchy code, not the FMA pipe. */
-template <class Src, class Sink, int TILE>
+template <class Src, class Sink, int TILE, bool GRID>
 __global__ void __launch_bounds__(TILE, 512 / TILE)
 k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, unsigned long long *n_states) {
     const size_t n = src.count();
     if (n == 0) return; /* dead bisection levels cost a launch, not a staging */
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    __shared__ uint32_t qn[4];          /* [1]: fill of q2 (convex narrowphase) */
+    __shared__ uint32_t qn[4];          /* [1]: fill of q2 (convex narrowphase), [3]: fill of the global spill area */
     __shared__ uint32_t wn1[TILE / 32]; /* fill of each warp's private region of q1 (quick) ... */
     __shared__ uint32_t wn3[TILE / 32]; /* ... and of q3 (mesh narrowphase) */
 
@@ -198,7 +223,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     const DJoint<float> *J = im.joints;
     const DGeom<float> *MG = im.mg;
     const DGeom<float> *SG = im.sg;
-    const uint32_t *PAIRS = im.pairs;
+    const uint32_t *PAIRS = im.t_pairs; /* the pipeline's list (without the pairs the static grid covers) */
     const SQuick *SQ = (const SQuick *)im.sq;
     const int *JG = im.jg_begin, *PA = im.pa_begin;
     const float4 *PS4 = (const float4 *)im.ps4;
@@ -217,7 +242,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             bulk_g2s(smem + cfg.off_joint, im.joints, (uint32_t)cfg.bytes_joint, &bar);
             bulk_g2s(smem + cfg.off_mg, im.mg, (uint32_t)cfg.bytes_mg, &bar);
             if (cfg.bytes_sg) bulk_g2s(smem + cfg.off_sg, im.sg, (uint32_t)cfg.bytes_sg, &bar);
-            if (cfg.bytes_pairs) bulk_g2s(smem + cfg.off_pairs, im.pairs, (uint32_t)cfg.bytes_pairs, &bar);
+            if (cfg.bytes_pairs) bulk_g2s(smem + cfg.off_pairs, im.t_pairs, (uint32_t)cfg.bytes_pairs, &bar);
             if (cfg.bytes_sq) bulk_g2s(smem + cfg.off_sq, im.sq, (uint32_t)cfg.bytes_sq, &bar);
             bulk_g2s(smem + cfg.off_jg, im.jg_begin, (uint32_t)cfg.bytes_jg, &bar);
             bulk_g2s(smem + cfg.off_pa, im.pa_begin, (uint32_t)cfg.bytes_pa, &bar);
@@ -232,12 +257,12 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         }
         J = (const DJoint<float> *)(smem + cfg.off_joint);
         MG = (const DGeom<float> *)(smem + cfg.off_mg);
-        SG = (const DGeom<float> *)(smem + cfg.off_sg);
-        PAIRS = (const uint32_t *)(smem + cfg.off_pairs);
-        SQ = (const SQuick *)(smem + cfg.off_sq);
+        if (cfg.bytes_sg) SG = (const DGeom<float> *)(smem + cfg.off_sg);
+        if (cfg.bytes_pairs) PAIRS = (const uint32_t *)(smem + cfg.off_pairs);
+        if (cfg.bytes_sq) SQ = (const SQuick *)(smem + cfg.off_sq);
         JG = (const int *)(smem + cfg.off_jg);
         PA = (const int *)(smem + cfg.off_pa);
-        PS4 = (const float4 *)(smem + cfg.off_ps4);
+        if (cfg.bytes_ps4) PS4 = (const float4 *)(smem + cfg.off_ps4);
     }
 
     float *slab = (float *)(smem + cfg.off_slab);       /* [n_mg*7][TILE] geometry poses */
@@ -254,6 +279,10 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_joint = im.n_joint, n_sub = im.n_sub;
     const float pad = Num<float>::eps() * 4.0f;
+    constexpr bool grid_on = GRID; /* compile-time: scenes without a static grid pay nothing for it */
+
+    uint32_t *spill = unc.spill + (size_t)blockIdx.x * unc.spill_cap;
+    auto spill_or_exact = [&](uint32_t item, bool mesh) { queue_overflow(unc, &qn[3], spill, unc_x, unc_y, item, mesh); };
 
     auto pose_at = [&](int g, int t) {
         const float *o = slab + (size_t)g * 7 * TILE + t;
@@ -268,6 +297,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         const typename Src::State st = src.prepare(s);
         const bool live = st.live && !im.static_hit;
         if (tid < 4) qn[tid] = 0;
+        if (lane == 0) { wn1[warp] = 0; wn3[warp] = 0; }
         f_hit[tid] = (st.live && im.static_hit) ? 1 : 0;
         {
             const uint2 it = src.unc_id(st);
@@ -318,13 +348,19 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                     auto enqueue = [&](int p, bool pass) {
                         const unsigned m = __ballot_sync(0xffffffffu, pass);
                         if (m) {
-                            const bool mesh = (PAIRS[p] >> 28) == PC_MESH;
-                            const uint32_t idx = (mesh ? n3 : n1) + __popc(m & lt_mask);
+                            const uint32_t w = PAIRS[p];
+                            const bool mesh = (w >> 28) == PC_MESH;
+                            uint32_t base = mesh ? n3 : n1;
+                            if (grid_on) { /* the divergent grid walk also appends: the fill counts live in shared memory */
+                                if (lane == 0) base = atomicAdd(mesh ? &wn3[warp] : &wn1[warp], (uint32_t)__popc(m));
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                            }
+                            const uint32_t idx = base + __popc(m & lt_mask);
                             if (pass) {
-                                const uint32_t item = ((uint32_t)tid << 20) | (uint32_t)p;
+                                const uint32_t item = item_pack(tid, a, (int)((w >> 8) & 0xffff), (int)((w >> 24) & 1));
                                 if (!mesh && idx < (uint32_t)cfg.q1_cap) q1w[idx] = item;
                                 else if (mesh && idx < (uint32_t)cfg.q3_cap) q3w[idx] = item;
-                                else unc_emit(unc, unc_x[tid], unc_y[tid], (uint32_t)p, TMK_WHOLE_PAIR); /* region full: decide it exactly */
+                                else spill_or_exact(item, mesh);
                             }
                             if (mesh) n3 += __popc(m); else n1 += __popc(m);
                         }
@@ -376,42 +412,74 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                         const float reach = ra + B.brad;
                         enqueue(p, live && dot(d, d) <= reach * reach);
                     }
+                    /* small static geometry of large scenes: walk the grid cells the bounding sphere can reach
+                     * (lane-divergent: every lane has its own cells) */
+                    if (grid_on && live) {
+                        const StaticGrid &G = im.grid;
+                        const float rq = ra + G.r_max;
+                        const int x0 = max(0, (int)floorf((ca.x - rq - G.ox) * G.inv_h)), x1 = min(G.nx - 1, (int)floorf((ca.x + rq - G.ox) * G.inv_h));
+                        const int y0 = max(0, (int)floorf((ca.y - rq - G.oy) * G.inv_h)), y1 = min(G.ny - 1, (int)floorf((ca.y + rq - G.oy) * G.inv_h));
+                        const int z0 = max(0, (int)floorf((ca.z - rq - G.oz) * G.inv_h)), z1 = min(G.nz - 1, (int)floorf((ca.z + rq - G.oz) * G.inv_h));
+                        const uint32_t *live_row = G.live + (size_t)a * G.wps;
+                        for (int z = z0; z <= z1; z++)
+                            for (int y = y0; y <= y1; y++) {
+                                const int row = (z * G.ny + y) * G.nx;
+                                const int k1 = G.cell_start[row + x1 + 1];
+                                for (int k = G.cell_start[row + x0]; k < k1; k++) { /* cells x0..x1 of a row are contiguous */
+                                    const int b = G.items[k];
+                                    if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
+                                    const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
+                                    const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+                                    const float reach = ra + c4.w;
+                                    if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
+                                    const uint32_t idx = atomicAdd(&wn1[warp], 1u);
+                                    const uint32_t item = item_pack(tid, a, b, 1);
+                                    if (idx < (uint32_t)cfg.q1_cap) q1w[idx] = item;
+                                    else spill_or_exact(item, false);
+                                }
+                            }
+                    }
                 }
             }
+            __syncwarp();
             if (lane == 0) {
-                wn1[warp] = min(n1, (uint32_t)cfg.q1_cap);
-                wn3[warp] = min(n3, (uint32_t)cfg.q3_cap);
+                wn1[warp] = min(grid_on ? wn1[warp] : n1, (uint32_t)cfg.q1_cap);
+                wn3[warp] = min(grid_on ? wn3[warp] : n3, (uint32_t)cfg.q3_cap);
             }
         }
         __syncthreads();
 
         /* ---- Q: quick certificates, one thread per surviving (state, pair) ---- */
         {
-            uint32_t total = 0;
-#pragma unroll
-            for (int k = 0; k < TILE / 32; k++) total += wn1[k];
-            for (uint32_t i = tid; i < total; i += TILE) {
-                /* dense index -> (warp region, offset) */
-                uint32_t off = i;
-                int k = 0;
-                while (off >= wn1[k]) { off -= wn1[k]; k++; }
-                const uint32_t e = q1[(size_t)k * cfg.q1_cap + off];
-                const int t = e >> 20, p = e & 0xfffff;
-                if (f_hit[t]) continue;
-                const uint32_t w = PAIRS[p];
-                const int a = w & 0xff, b = (w >> 8) & 0xffff;
+            auto quick_item = [&](const uint32_t e) {
+                const int t = ITEM_T(e), a = ITEM_A(e), b = ITEM_B(e);
+                if (f_hit[t]) return;
                 const DGeom<float> &A = MG[a];
                 const QG qa = qg_from_pose(A, pose_at(a, t));
                 int r;
-                if ((w >> 24) & 1) r = quick_pair(A.shape, qa, (int)((w >> 25) & 7), qg_from_static(SQ[b]));
+                if (ITEM_STATIC(e)) r = quick_pair(A.shape, qa, SG[b].shape, qg_from_static(SQ[b]));
                 else r = quick_pair(A.shape, qa, MG[b].shape, qg_from_pose(MG[b], pose_at(b, t)));
                 if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
+                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], ITEM_KEY(e), TMK_WHOLE_PAIR);
                 else if (r == NEED) {
                     const uint32_t idx = atomicAdd(&qn[1], 1u);
                     if (idx < (uint32_t)cfg.q2_cap) q2[idx] = e;
-                    else unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
+                    else unc_emit(unc, unc_x[t], unc_y[t], ITEM_KEY(e), TMK_WHOLE_PAIR);
                 }
+            };
+            uint32_t total = 0;
+#pragma unroll
+            for (int k = 0; k < TILE / 32; k++) total += wn1[k];
+            const uint32_t n_spill = min(qn[3], unc.spill_cap);
+            for (uint32_t i = tid; i < total + n_spill; i += TILE) {
+                uint32_t e;
+                if (i < total) { /* dense index -> (warp region, offset) */
+                    uint32_t off = i;
+                    int k = 0;
+                    while (off >= wn1[k]) { off -= wn1[k]; k++; }
+                    e = q1[(size_t)k * cfg.q1_cap + off];
+                } else e = spill[i - total];
+                quick_item(e);
             }
         }
         __syncthreads();
@@ -421,17 +489,15 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             const uint32_t cnt = min(qn[1], (uint32_t)cfg.q2_cap);
             for (uint32_t i = tid; i < cnt; i += TILE) {
                 const uint32_t e = q2[i];
-                const int t = e >> 20, p = e & 0xfffff;
+                const int t = ITEM_T(e), a = ITEM_A(e), b = ITEM_B(e);
                 if (f_hit[t]) continue;
-                const uint32_t w = PAIRS[p];
-                const int a = w & 0xff, b = (w >> 8) & 0xffff;
                 const DGeom<float> *B;
                 Xf<float> XB;
-                if ((w >> 24) & 1) { B = &SG[b]; XB = xload(B->tf); }
+                if (ITEM_STATIC(e)) { B = &SG[b]; XB = xload(B->tf); }
                 else { B = &MG[b]; XB = pose_at(b, t); }
                 const int r = test_convex(shape_of(MG[a]), pose_at(a, t), shape_of(*B), XB);
                 if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
+                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], ITEM_KEY(e), TMK_WHOLE_PAIR);
             }
         }
         __syncthreads();
@@ -446,19 +512,17 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                 int k = 0;
                 while (off >= wn3[k]) { off -= wn3[k]; k++; }
                 const uint32_t e = q3[(size_t)k * cfg.q3_cap + off];
-                const int t = e >> 20, p = e & 0xfffff;
+                const int t = ITEM_T(e), a = ITEM_A(e), b = ITEM_B(e);
                 if (f_hit[t]) continue;
-                const uint32_t w = PAIRS[p];
-                const int a = w & 0xff, b = (w >> 8) & 0xffff;
                 const DGeom<float> *B;
                 Xf<float> XB;
-                if ((w >> 24) & 1) { B = &SG[b]; XB = xload(B->tf); }
+                if (ITEM_STATIC(e)) { B = &SG[b]; XB = xload(B->tf); }
                 else { B = &MG[b]; XB = pose_at(b, t); }
                 TriEmit on_tri;
-                on_tri.u = unc; on_tri.id_x = unc_x[t]; on_tri.id_y = unc_y[t]; on_tri.pair = (uint32_t)p;
+                on_tri.u = unc; on_tri.id_x = unc_x[t]; on_tri.id_y = unc_y[t]; on_tri.pair = ITEM_KEY(e);
                 const int r = test_geoms(MG[a], pose_at(a, t), *B, XB, im.meshes, on_tri);
                 if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], (uint32_t)p, TMK_WHOLE_PAIR);
+                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], ITEM_KEY(e), TMK_WHOLE_PAIR);
             }
         }
         __syncthreads();
@@ -482,11 +546,10 @@ __global__ void __launch_bounds__(128) k_recheck_items(Image<double> im, Src src
         for (int k = 0; k < im.n_sub; k++) q[k] = src.template load1<double>(st, k);
         Xf<double> gp[TMK_MAXMG];
         fk_config(im, q, gp);
-        const uint32_t w = im.pairs[pair];
-        const int a = w & 0xff, b = (w >> 8) & 0xffff;
+        const int a = ITEM_A(pair), b = ITEM_B(pair);
         const DGeom<double> &A = im.mg[a];
-        const DGeom<double> &B = (w >> 24) & 1 ? im.sg[b] : im.mg[b];
-        const Xf<double> XB = (w >> 24) & 1 ? xload(B.tf) : gp[b];
+        const DGeom<double> &B = ITEM_STATIC(pair) ? im.sg[b] : im.mg[b];
+        const Xf<double> XB = ITEM_STATIC(pair) ? xload(B.tf) : gp[b];
         int r;
         if (it.w == TMK_WHOLE_PAIR) r = test_geoms(A, gp[a], B, XB, im.meshes);
         else if (A.shape == K_MESH) r = test_mesh_tri_shape(im.meshes[A.mesh], gp[a], shape_of(B), XB, (int)it.w);
@@ -575,7 +638,7 @@ __global__ void k_edges_finish(const int32_t *first, uint32_t n_edge, uint32_t *
 
 static inline int align16(int x) { return (x + 15) & ~15; }
 
-#define TMK_STAGE_BUDGET (40 * 1024) /* images up to this size are staged in shared memory */
+#define TMK_STAGE_BUDGET (48 * 1024) /* shared memory the staged part of the image may take */
 
 /* shared-memory plan for one (kernel, tile) choice; returns resident warps per SM (0 = does not fit) */
 template <class Kernel>
@@ -585,14 +648,23 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
     cfg.bytes_joint = align16(im.n_joint * (int)sizeof(DJoint<float>));
     cfg.bytes_mg = align16(im.n_mg * (int)sizeof(DGeom<float>));
     cfg.bytes_sg = align16(im.n_sg * (int)sizeof(DGeom<float>));
-    cfg.bytes_pairs = align16(im.n_pair * 4);
+    cfg.bytes_pairs = align16(im.n_tpair * 4);
     cfg.bytes_sq = align16(im.n_sg * (int)sizeof(SQuick));
     cfg.bytes_jg = align16((im.n_joint + 1) * 4);
     cfg.bytes_pa = align16((3 * im.n_mg + 1) * 4);
-    cfg.bytes_ps4 = im.n_pair * 16;
-    int image = cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_sg + cfg.bytes_pairs + cfg.bytes_sq + cfg.bytes_jg + cfg.bytes_pa +
-                cfg.bytes_ps4;
-    cfg.stage = image <= TMK_STAGE_BUDGET ? 1 : 0;
+    cfg.bytes_ps4 = im.n_tpair * 16;
+    /* staging policy: everything if it fits the budget; else leave the static geometry table (only read by
+     * the narrowphase phases) in global memory; else the quick table too; else nothing */
+    {
+        const int small = cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_jg + cfg.bytes_pa;
+        const int lists = cfg.bytes_pairs + cfg.bytes_ps4;
+        cfg.stage = 1;
+        if (small + lists + cfg.bytes_sq + cfg.bytes_sg <= TMK_STAGE_BUDGET) { /* all */
+        } else if (small + lists + cfg.bytes_sq <= TMK_STAGE_BUDGET) cfg.bytes_sg = 0;
+        else if (small + lists <= TMK_STAGE_BUDGET) cfg.bytes_sg = cfg.bytes_sq = 0;
+        else if (small <= TMK_STAGE_BUDGET) cfg.bytes_sg = cfg.bytes_sq = cfg.bytes_pairs = cfg.bytes_ps4 = 0;
+        else cfg.stage = 0;
+    }
     int off = 0;
     cfg.off_joint = off; off += cfg.stage ? cfg.bytes_joint : 0;
     cfg.off_mg = off; off += cfg.stage ? cfg.bytes_mg : 0;
