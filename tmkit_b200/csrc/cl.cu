@@ -208,7 +208,7 @@ struct aa_rx_cl {
     ImageDev img;
 
     /* batch scratch */
-    DBuf d_spill;
+    DBuf d_spill, d_mesh;
     DBuf d_q, d_q1, d_bits, d_unc, d_cnt, d_first, d_pairhit, d_stats, d_nd, d_alive0, d_alive1, d_efirst;
     uint32_t *h_cnt; /* pinned */
     int track, stats_on;
@@ -328,7 +328,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     if (!cl) return;
     cudaStreamSynchronize(cl->stream);
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
-                    &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
+                    &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
                     &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4, &cl->img.tpairs, &cl->img.g_cells, &cl->img.g_items,
                     &cl->img.g_live};
@@ -786,8 +786,8 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     u.cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states / 2), 0x7fffffffu);
     if (const char *e = getenv("TMK_UNC_CAP")) u.cap = (uint32_t)std::max(1, atoi(e)); /* test aid: forces k_overflow_all */
     cl->d_unc.need(sizeof(uint4) * (size_t)u.cap);
-    cl->d_cnt.need(128);
-    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 128, s));
+    cl->d_cnt.need(256);
+    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 256, s));
     u.items = (uint4 *)cl->d_unc.p;
     u.n = (uint32_t *)cl->d_cnt.p;
     u.overflow = (uint32_t *)cl->d_cnt.p + 1;
@@ -797,6 +797,12 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     const size_t ctas = (size_t)std::max(std::max(cl->img.wcfg.grid, cl->img.wcfg_e.grid), 1);
     cl->d_spill.need(sizeof(uint32_t) * ctas * (size_t)std::max<uint32_t>(u.spill_cap, 1));
     u.spill = (uint32_t *)cl->d_spill.p;
+    /* exported mesh items: room for 1.5 per state (more than that: the exact re-check takes them) */
+    u.mesh_cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states + n_states / 2), 0x3fffffffu);
+    if (const char *e = getenv("TMK_MESH_CAP")) u.mesh_cap = (uint32_t)std::max(0, atoi(e)); /* test aid */
+    cl->d_mesh.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.mesh_cap, 1));
+    u.mesh_items = (float4 *)cl->d_mesh.p;
+    u.mesh_n = (uint32_t *)cl->d_cnt.p + 4; /* d_cnt: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [8+L] alive, [32+L] mesh items of edge level L */
     return u;
 }
 
@@ -832,14 +838,16 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         CK(cudaGetLastError());
         cl->stats.n_launches += 1;
         if (c_end < n_cfg) return;
-        if (ev) CK(cudaEventRecord(ev[1], s));
         src.n = n_cfg; src.s_begin = 0;
+        k_mesh_items<SrcConfigs, SinkBits><<<148 * 16, 128, 0, s>>>(im.f, src, sink, u);
+        CK(cudaGetLastError());
+        if (ev) CK(cudaEventRecord(ev[1], s));
         k_recheck_items<SrcConfigs, SinkBits><<<148, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         k_overflow_all<SrcConfigs, SinkBits><<<148 * 2, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         if (ev) CK(cudaEventRecord(ev[2], s));
-        cl->stats.n_launches += 2;
+        cl->stats.n_launches += 3;
         return;
     }
     if (chunk_begin != 0 || (chunk_end && chunk_end < n_cfg)) tmk_die("internal: chunked launch on the instrumented path");
@@ -896,10 +904,13 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         size_t launches = 1;
         for (int L = 0; L < TMK_EDGE_LEVELS; L++) {
             src.alive = cur_alive; src.n_alive = cur_n; src.level = L;
+            u.mesh_n = cnt + 32 + L;
             launch_tile<SrcEdgeLevel, SinkEdgeFirst>(im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2),
                                                      (unsigned)im.wcfg_e.grid, s);
             CK(cudaGetLastError());
-            launches++;
+            k_mesh_items<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
+            CK(cudaGetLastError());
+            launches += 2;
             if (L + 1 < TMK_EDGE_LEVELS) {
                 uint32_t *out = alive[L & 1], *n_out = cnt + 8 + L;
                 k_edges_compact<<<148 * 2, 256, 0, s>>>(cur_alive, cur_n, ne, nd, first, L, out, n_out);
@@ -1126,6 +1137,17 @@ extern "C" double tmk_fp32_peak_tflops(void) {
     cudaFree(d);
     return best;
 }
+
+#ifdef TMK_PHASE_CLOCKS
+extern "C" void tmk_phase_cycles(unsigned long long *out, int reset) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, tmk::g_phase_cycles, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        CK(cudaMemcpyToSymbol(tmk::g_phase_cycles, z, sizeof(z)));
+    }
+}
+#endif
 
 extern "C" void aa_rx_cl_kernel_timing(struct aa_rx_cl *cl, int enable) {
     cl->timing = enable ? 1 : 0;

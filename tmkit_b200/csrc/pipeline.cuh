@@ -87,7 +87,13 @@ struct UncList {
     uint32_t *overflow; /* set when an item was dropped: the brute-force double kernel then runs */
     uint32_t *spill;    /* per-CTA overflow area of the broadphase queue in global memory: [gridDim.x][spill_cap] */
     uint32_t spill_cap;
+    /* deferred mesh narrowphase: the pipeline exports its surviving mesh items (with the poses they need)
+     * and k_mesh_items runs them with far more items in flight per SM than a phase of the tile loop can */
+    float4 *mesh_items; /* TMK_MESH_REC float4 per item */
+    uint32_t *mesh_n;
+    uint32_t mesh_cap;
 };
+#define TMK_MESH_REC 5 /* float4 per exported mesh item: (id_x, id_y, key, -) poseA[7] - poseB[7] - */
 #define TMK_WHOLE_PAIR 0xffffffffu
 __device__ __forceinline__ void unc_emit(const UncList &u, uint32_t id_x, uint32_t id_y, uint32_t pair, uint32_t tri) {
     uint32_t i = atomicAdd(u.n, 1u);
@@ -204,6 +210,21 @@ struct SinkEdgeFirst {
     }
 };
 
+#ifdef TMK_PHASE_CLOCKS
+/* tuning aid (not in the product build): cycles per phase, summed over CTAs by thread 0 */
+__device__ unsigned long long g_phase_cycles[8];
+#define PHASE_MARK(k)                                                   \
+    do {                                                                \
+        if (tid == 0) {                                                 \
+            const long long now_ = clock64();                           \
+            atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - t_phase)); \
+            t_phase = now_;                                             \
+        }                                                               \
+    } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
+
 /* ------------------------------------------------------------------ the kernel
  * TILE threads = TILE states per CTA pass; phases are CTA-synchronous so that all warps of an SM
  * execute the same (small) code region at a time - the instruction caches (L0 6 KB, L1.5 32 KB)
@@ -292,6 +313,9 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         return X;
     };
 
+#ifdef TMK_PHASE_CLOCKS
+    long long t_phase = clock64();
+#endif
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t s = tile * TILE + tid;
         const typename Src::State st = src.prepare(s);
@@ -310,6 +334,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             if (lane == 0 && lm) atomicAdd(n_states, (unsigned long long)__popc(lm));
         }
         __syncthreads();
+        PHASE_MARK(0);
 
         /* ---- P1 + P2: joint chain in registers; every moving geometry meets its partner list at once ---- */
         {
@@ -448,6 +473,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             }
         }
         __syncthreads();
+        PHASE_MARK(1);
 
         /* ---- Q: quick certificates, one thread per surviving (state, pair) ---- */
         {
@@ -483,6 +509,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             }
         }
         __syncthreads();
+        PHASE_MARK(2);
 
         /* ---- G: convex narrowphase (SAT / GJK) on what the certificates left open ---- */
         {
@@ -501,34 +528,82 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             }
         }
         __syncthreads();
+        PHASE_MARK(3);
 
-        /* ---- M: mesh narrowphase (BVH traversal) ---- */
+        /* ---- X: export the mesh items of states that are still undecided (BVH traversal is a chain of
+         * dependent loads: as a phase of this loop it was half of the tile time at 12 % of the
+         * instructions; k_mesh_items hides that latency with items instead of idling warps) ---- */
         {
             uint32_t total = 0;
 #pragma unroll
             for (int k = 0; k < TILE / 32; k++) total += wn3[k];
-            for (uint32_t i = tid; i < total; i += TILE) {
-                uint32_t off = i;
-                int k = 0;
-                while (off >= wn3[k]) { off -= wn3[k]; k++; }
-                const uint32_t e = q3[(size_t)k * cfg.q3_cap + off];
-                const int t = ITEM_T(e), a = ITEM_A(e), b = ITEM_B(e);
-                if (f_hit[t]) continue;
-                const DGeom<float> *B;
-                Xf<float> XB;
-                if (ITEM_STATIC(e)) { B = &SG[b]; XB = xload(B->tf); }
-                else { B = &MG[b]; XB = pose_at(b, t); }
-                TriEmit on_tri;
-                on_tri.u = unc; on_tri.id_x = unc_x[t]; on_tri.id_y = unc_y[t]; on_tri.pair = ITEM_KEY(e);
-                const int r = test_geoms(MG[a], pose_at(a, t), *B, XB, im.meshes, on_tri);
-                if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], ITEM_KEY(e), TMK_WHOLE_PAIR);
+            for (uint32_t base = 0; base < total; base += TILE) { /* uniform trip count: the ballots are convergent */
+                const uint32_t i = base + tid;
+                bool keep = false;
+                uint32_t e = 0;
+                if (i < total) {
+                    uint32_t off = i;
+                    int k = 0;
+                    while (off >= wn3[k]) { off -= wn3[k]; k++; }
+                    e = q3[(size_t)k * cfg.q3_cap + off];
+                    keep = f_hit[ITEM_T(e)] == 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                uint32_t dst = 0;
+                if (lane == 0 && m) dst = atomicAdd(unc.mesh_n, (uint32_t)__popc(m));
+                dst = __shfl_sync(0xffffffffu, dst, 0) + __popc(m & lt_mask);
+                if (keep) {
+                    const int t = ITEM_T(e);
+                    if (dst < unc.mesh_cap) {
+                        const Xf<float> XA = pose_at(ITEM_A(e), t);
+                        Xf<float> XB = XA;
+                        if (!ITEM_STATIC(e)) XB = pose_at(ITEM_B(e), t);
+                        float4 *rec = unc.mesh_items + (size_t)dst * TMK_MESH_REC;
+                        rec[0] = make_float4(__uint_as_float(unc_x[t]), __uint_as_float(unc_y[t]), __uint_as_float(ITEM_KEY(e)), 0.f);
+                        rec[1] = make_float4(XA.r.x, XA.r.y, XA.r.z, XA.r.w);
+                        rec[2] = make_float4(XA.v.x, XA.v.y, XA.v.z, XB.v.x);
+                        rec[3] = make_float4(XB.r.x, XB.r.y, XB.r.z, XB.r.w);
+                        rec[4] = make_float4(XB.v.y, XB.v.z, 0.f, 0.f);
+                    } else unc_emit(unc, unc_x[t], unc_y[t], ITEM_KEY(e), TMK_WHOLE_PAIR); /* list full: decide it exactly */
+                }
             }
         }
         __syncthreads();
+        PHASE_MARK(4);
 
         sink.emit(st, tile * (TILE / 32) + warp, f_hit[tid] != 0 || !st.live, lane);
         __syncthreads();
+        PHASE_MARK(5);
+    }
+}
+
+/* deferred mesh narrowphase: one thread per exported item */
+template <class Src, class Sink>
+__global__ void __launch_bounds__(128) k_mesh_items(Image<float> im, Src src, Sink sink, UncList unc) {
+    uint32_t n = *unc.mesh_n;
+    if (n > unc.mesh_cap) n = unc.mesh_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 *rec = unc.mesh_items + (size_t)i * TMK_MESH_REC;
+        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
+        const uint32_t id_x = __float_as_uint(r0.x), id_y = __float_as_uint(r0.y), key = __float_as_uint(r0.z);
+        Xf<float> XA, XB;
+        XA.r.x = r1.x; XA.r.y = r1.y; XA.r.z = r1.z; XA.r.w = r1.w;
+        XA.v.x = r2.x; XA.v.y = r2.y; XA.v.z = r2.z;
+        const DGeom<float> &A = im.mg[ITEM_A(key)];
+        const DGeom<float> *B;
+        if (ITEM_STATIC(key)) {
+            B = &im.sg[ITEM_B(key)];
+            XB = xload(B->tf);
+        } else {
+            B = &im.mg[ITEM_B(key)];
+            XB.r.x = r3.x; XB.r.y = r3.y; XB.r.z = r3.z; XB.r.w = r3.w;
+            XB.v.x = r2.w; XB.v.y = r4.x; XB.v.z = r4.y;
+        }
+        TriEmit on_tri;
+        on_tri.u = unc; on_tri.id_x = id_x; on_tri.id_y = id_y; on_tri.pair = key;
+        const int r = test_geoms(A, XA, *B, XB, im.meshes, on_tri);
+        if (r == HIT) sink.mark_hit(src.from_id(id_x, id_y));
+        else if (r == UNC) unc_emit(unc, id_x, id_y, key, TMK_WHOLE_PAIR);
     }
 }
 
