@@ -839,7 +839,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         cl->stats.n_launches += 1;
         if (c_end < n_cfg) return;
         src.n = n_cfg; src.s_begin = 0;
-        k_mesh_items<SrcConfigs, SinkBits><<<148 * 16, 128, 0, s>>>(im.f, src, sink, u);
+        k_heavy_items<SrcConfigs, SinkBits><<<148 * 16, 128, 0, s>>>(im.f, src, sink, u);
         CK(cudaGetLastError());
         if (ev) CK(cudaEventRecord(ev[1], s));
         k_recheck_items<SrcConfigs, SinkBits><<<148, 128, 0, s>>>(im.d, src, sink, u);
@@ -908,7 +908,7 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
             launch_tile<SrcEdgeLevel, SinkEdgeFirst>(im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2),
                                                      (unsigned)im.wcfg_e.grid, s);
             CK(cudaGetLastError());
-            k_mesh_items<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
+            k_heavy_items<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
             CK(cudaGetLastError());
             launches += 2;
             if (L + 1 < TMK_EDGE_LEVELS) {

@@ -88,7 +88,7 @@ struct UncList {
     uint32_t *spill;    /* per-CTA overflow area of the broadphase queue in global memory: [gridDim.x][spill_cap] */
     uint32_t spill_cap;
     /* deferred mesh narrowphase: the pipeline exports its surviving mesh items (with the poses they need)
-     * and k_mesh_items runs them with far more items in flight per SM than a phase of the tile loop can */
+     * and k_heavy_items runs them with far more items in flight per SM than a phase of the tile loop can */
     float4 *mesh_items; /* TMK_MESH_REC float4 per item */
     uint32_t *mesh_n;
     uint32_t mesh_cap;
@@ -511,43 +511,28 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         __syncthreads();
         PHASE_MARK(2);
 
-        /* ---- G: convex narrowphase (SAT / GJK) on what the certificates left open ---- */
+        /* ---- X: export the heavy items - pairs the certificates left open (SAT / GJK) and mesh pairs (BVH
+         * traversal) - of states that are still undecided.  As phases of this loop they were 60 % of the
+         * tile time at 25 % of the instructions (few items, long dependent chains, everybody else waiting
+         * at the barrier); k_heavy_items runs them with thousands of items in flight per SM ---- */
         {
-            const uint32_t cnt = min(qn[1], (uint32_t)cfg.q2_cap);
-            for (uint32_t i = tid; i < cnt; i += TILE) {
-                const uint32_t e = q2[i];
-                const int t = ITEM_T(e), a = ITEM_A(e), b = ITEM_B(e);
-                if (f_hit[t]) continue;
-                const DGeom<float> *B;
-                Xf<float> XB;
-                if (ITEM_STATIC(e)) { B = &SG[b]; XB = xload(B->tf); }
-                else { B = &MG[b]; XB = pose_at(b, t); }
-                const int r = test_convex(shape_of(MG[a]), pose_at(a, t), shape_of(*B), XB);
-                if (r == HIT) f_hit[t] = 1;
-                else if (r == UNC) unc_emit(unc, unc_x[t], unc_y[t], ITEM_KEY(e), TMK_WHOLE_PAIR);
-            }
-        }
-        __syncthreads();
-        PHASE_MARK(3);
-
-        /* ---- X: export the mesh items of states that are still undecided (BVH traversal is a chain of
-         * dependent loads: as a phase of this loop it was half of the tile time at 12 % of the
-         * instructions; k_mesh_items hides that latency with items instead of idling warps) ---- */
-        {
-            uint32_t total = 0;
+            uint32_t total3 = 0;
 #pragma unroll
-            for (int k = 0; k < TILE / 32; k++) total += wn3[k];
+            for (int k = 0; k < TILE / 32; k++) total3 += wn3[k];
+            const uint32_t total2 = min(qn[1], (uint32_t)cfg.q2_cap);
+            const uint32_t total = total2 + total3;
             for (uint32_t base = 0; base < total; base += TILE) { /* uniform trip count: the ballots are convergent */
                 const uint32_t i = base + tid;
                 bool keep = false;
                 uint32_t e = 0;
-                if (i < total) {
-                    uint32_t off = i;
+                if (i < total2) e = q2[i];
+                else if (i < total) {
+                    uint32_t off = i - total2;
                     int k = 0;
                     while (off >= wn3[k]) { off -= wn3[k]; k++; }
                     e = q3[(size_t)k * cfg.q3_cap + off];
-                    keep = f_hit[ITEM_T(e)] == 0;
                 }
+                if (i < total) keep = f_hit[ITEM_T(e)] == 0;
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 uint32_t dst = 0;
                 if (lane == 0 && m) dst = atomicAdd(unc.mesh_n, (uint32_t)__popc(m));
@@ -577,9 +562,9 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     }
 }
 
-/* deferred mesh narrowphase: one thread per exported item */
+/* deferred narrowphase (SAT / GJK / mesh BVH): one thread per exported item */
 template <class Src, class Sink>
-__global__ void __launch_bounds__(128) k_mesh_items(Image<float> im, Src src, Sink sink, UncList unc) {
+__global__ void __launch_bounds__(128) k_heavy_items(Image<float> im, Src src, Sink sink, UncList unc) {
     uint32_t n = *unc.mesh_n;
     if (n > unc.mesh_cap) n = unc.mesh_cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
