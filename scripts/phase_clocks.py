@@ -17,5 +17,5 @@ for rep in range(3):
     cl.sync()
     L.tmk_phase_cycles(out, 1)
 v = np.array(list(out)[:6], dtype=float)
-names = ["load q", "P1+P2", "Q", "G", "M", "emit"]
+names = ["load q", "P1+P2", "Q", "-", "export", "emit"]
 print({k: f"{100*x/v.sum():.1f}%" for k, x in zip(names, v)}, "cycles per tile per CTA:", v.sum() / (n / 256))

@@ -414,8 +414,8 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                         enqueue(p, live && dx * dx + dy * dy + dz * dz <= reach * reach);
                     }
                     /* static boxes: bounding sphere of A against the box itself (exact point-box distance) */
-                    for (; p < e1; p++) {
-                        const int b = (PAIRS[p] >> 8) & 0xffff;
+                    auto box_pass = [&](int pp) {
+                        const int b = (PAIRS[pp] >> 8) & 0xffff;
                         const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
                         const float4 x4 = *reinterpret_cast<const float4 *>(&SQ[b].a0x);
                         const float4 y4 = *reinterpret_cast<const float4 *>(&SQ[b].a1x);
@@ -424,8 +424,13 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                         const float ex = fmaxf(fabsf(dx * x4.x + dy * x4.y + dz * x4.z) - x4.w, 0.f);
                         const float ey = fmaxf(fabsf(dx * y4.x + dy * y4.y + dz * y4.z) - y4.w, 0.f);
                         const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
-                        enqueue(p, live && ex * ex + ey * ey + ez * ez <= ra * ra);
+                        return live && ex * ex + ey * ey + ez * ez <= ra * ra;
+                    };
+                    for (; p + 2 <= e1; p += 2) {
+                        const bool p0 = box_pass(p), p1 = box_pass(p + 1);
+                        if (__any_sync(0xffffffffu, p0 | p1)) { enqueue(p, p0); enqueue(p + 1, p1); }
                     }
+                    for (; p < e1; p++) enqueue(p, box_pass(p));
                     /* moving partners (their poses are already in the slab) */
                     for (; p < e2; p++) {
                         const int b = (PAIRS[p] >> 8) & 0xffff;
@@ -562,9 +567,12 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     }
 }
 
+#ifndef HEAVY_MIN_CTAS
+#define HEAVY_MIN_CTAS 4
+#endif
 /* deferred narrowphase (SAT / GJK / mesh BVH): one thread per exported item */
 template <class Src, class Sink>
-__global__ void __launch_bounds__(128) k_heavy_items(Image<float> im, Src src, Sink sink, UncList unc) {
+__global__ void __launch_bounds__(128, HEAVY_MIN_CTAS) k_heavy_items(Image<float> im, Src src, Sink sink, UncList unc) {
     uint32_t n = *unc.mesh_n;
     if (n > unc.mesh_cap) n = unc.mesh_cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
