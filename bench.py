@@ -368,11 +368,13 @@ def main():
         cl.kernel_timing(True)  # events around the dominant kernel, recorded by the library on `stream`
         barrier()
         ev[0].record(ts)
+        t_host = time.perf_counter()
         for i in range(args.steps):
             step(args.warmup + i)
             if rank == 0 and i % 16 == 8:
                 sampler.sample_now()  # while the GPU is busy with the steps already queued
         ev[1].record(ts)
+        host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps
         barrier()
         ms_total = ev[0].elapsed_time(ev[1])
         n_timed, k_ms_sum, rk_ms_sum = cl.kernel_time()
@@ -472,6 +474,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "aa_rx_cl_check_edges" if edges else "aa_rx_cl_check_batch", "host_dtype": "f64 rows, pinned"},
         "gpu_launches": int(launches_per_step * args.steps),
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
         # the path is bound by the FP32 (FMA) pipe, not HBM and not the tensor cores (SURVEY.md 8d,
         # DESIGN.md): `roofline` is the FP32 one, `roofline_hbm` the contract's HBM form beside it

@@ -208,7 +208,7 @@ struct aa_rx_cl {
     ImageDev img;
 
     /* batch scratch */
-    DBuf d_spill, d_mesh;
+    DBuf d_spill, d_mesh, d_conv, d_tri;
     DBuf d_q, d_q1, d_bits, d_unc, d_cnt, d_first, d_pairhit, d_stats, d_nd, d_alive0, d_alive1, d_efirst;
     uint32_t *h_cnt; /* pinned */
     int track, stats_on;
@@ -328,7 +328,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     if (!cl) return;
     cudaStreamSynchronize(cl->stream);
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
-                    &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
+                    &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_conv, &cl->d_tri, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
                     &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4, &cl->img.tpairs, &cl->img.g_cells, &cl->img.g_items,
                     &cl->img.g_live};
@@ -781,13 +781,26 @@ static void launch_tile(const Image<float> &f, const TileCfg &cfg, const Src &sr
     }
 }
 
+/* the deferred narrowphase: convex pairs, mesh traversal, open triangles (in this order: the triangle
+ * list is filled by the traversal) */
+template <class Src, class Sink>
+static void launch_heavy(const Image<float> &f, const Src &src, const Sink &sink, const UncList &u, unsigned ctas,
+                         cudaStream_t s) {
+    k_conv_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
+    CK(cudaGetLastError());
+    k_mesh_traverse<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
+    CK(cudaGetLastError());
+    k_tri_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
+    CK(cudaGetLastError());
+}
+
 static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     UncList u;
     u.cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states / 2), 0x7fffffffu);
     if (const char *e = getenv("TMK_UNC_CAP")) u.cap = (uint32_t)std::max(1, atoi(e)); /* test aid: forces k_overflow_all */
     cl->d_unc.need(sizeof(uint4) * (size_t)u.cap);
-    cl->d_cnt.need(256);
-    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 256, s));
+    cl->d_cnt.need(512);
+    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 512, s));
     u.items = (uint4 *)cl->d_unc.p;
     u.n = (uint32_t *)cl->d_cnt.p;
     u.overflow = (uint32_t *)cl->d_cnt.p + 1;
@@ -802,7 +815,18 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     if (const char *e = getenv("TMK_MESH_CAP")) u.mesh_cap = (uint32_t)std::max(0, atoi(e)); /* test aid */
     cl->d_mesh.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.mesh_cap, 1));
     u.mesh_items = (float4 *)cl->d_mesh.p;
-    u.mesh_n = (uint32_t *)cl->d_cnt.p + 4; /* d_cnt: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [8+L] alive, [32+L] mesh items of edge level L */
+    /* d_cnt words: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [5] convex items, [6] triangles,
+     * [8+L] alive edges of level L, [32+L] / [48+L] / [64+L] mesh / convex / triangle items of edge level L */
+    u.mesh_n = (uint32_t *)cl->d_cnt.p + 4;
+    u.conv_cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states), 0x3fffffffu);
+    u.tri_cap = u.conv_cap;
+    if (const char *e = getenv("TMK_MESH_CAP")) u.conv_cap = u.tri_cap = u.mesh_cap;
+    cl->d_conv.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.conv_cap, 1));
+    cl->d_tri.need(sizeof(uint2) * (size_t)std::max<uint32_t>(u.tri_cap, 1));
+    u.conv_items = (float4 *)cl->d_conv.p;
+    u.conv_n = (uint32_t *)cl->d_cnt.p + 5;
+    u.tri_items = (uint2 *)cl->d_tri.p;
+    u.tri_n = (uint32_t *)cl->d_cnt.p + 6;
     return u;
 }
 
@@ -839,15 +863,14 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         cl->stats.n_launches += 1;
         if (c_end < n_cfg) return;
         src.n = n_cfg; src.s_begin = 0;
-        k_heavy_items<SrcConfigs, SinkBits><<<148 * 16, 128, 0, s>>>(im.f, src, sink, u);
-        CK(cudaGetLastError());
+        launch_heavy<SrcConfigs, SinkBits>(im.f, src, sink, u, 148 * 16, s);
         if (ev) CK(cudaEventRecord(ev[1], s));
         k_recheck_items<SrcConfigs, SinkBits><<<148, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         k_overflow_all<SrcConfigs, SinkBits><<<148 * 2, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         if (ev) CK(cudaEventRecord(ev[2], s));
-        cl->stats.n_launches += 3;
+        cl->stats.n_launches += 5;
         return;
     }
     if (chunk_begin != 0 || (chunk_end && chunk_end < n_cfg)) tmk_die("internal: chunked launch on the instrumented path");
@@ -904,11 +927,11 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         size_t launches = 1;
         for (int L = 0; L < TMK_EDGE_LEVELS; L++) {
             src.alive = cur_alive; src.n_alive = cur_n; src.level = L;
-            u.mesh_n = cnt + 32 + L;
+            u.mesh_n = cnt + 32 + L; u.conv_n = cnt + 48 + L; u.tri_n = cnt + 64 + L;
             launch_tile<SrcEdgeLevel, SinkEdgeFirst>(im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2),
                                                      (unsigned)im.wcfg_e.grid, s);
             CK(cudaGetLastError());
-            k_heavy_items<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
+            k_heavy_mixed<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
             CK(cudaGetLastError());
             launches += 2;
             if (L + 1 < TMK_EDGE_LEVELS) {

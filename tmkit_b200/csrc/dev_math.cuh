@@ -781,9 +781,12 @@ TMK_HD int test_mesh_tri_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape
 }
 
 /* shape S (sphere/box/cyl, pose XS) against mesh (pose XM) */
-template <typename T, class UncTri = NoTri>
+/* UncTri: what to do with a triangle the FP32 tests cannot decide.  NeedTri: what to do with a
+ * triangle the quick certificates leave open - by default it is decided here (GJK); the wavefront
+ * kernels record it instead so that the traversal stays short and uniform. */
+template <typename T, class UncTri = NoTri, class NeedTri = NoTri>
 TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> &S, const Xf<T> &XS, T s_brad,
-                           unsigned *n_leaf = nullptr, UncTri on_unc_tri = UncTri()) {
+                           unsigned *n_leaf = nullptr, UncTri on_unc_tri = UncTri(), NeedTri on_need_tri = NeedTri()) {
     Xf<T> s_in_m = xrel(XM, XS); /* S in mesh frame */
     Xf<T> m_in_s = xrel(XS, XM); /* mesh in S frame */
     Mat3<T> Rms = q2m(m_in_s.r);
@@ -830,7 +833,10 @@ TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> 
                 if (S.kind == K_SPHERE) r = test_tri_vs_shape(S, p0, p1, p2);
                 else {
                     r = quick_tri(S, p0, p1, p2);
-                    if (r == NEED) r = test_tri_vs_shape(S, p0, p1, p2);
+                    if (r == NEED) {
+                        if (NeedTri::enabled) { on_need_tri(nd.a + k); r = SEP; }
+                        else r = test_tri_vs_shape(S, p0, p1, p2);
+                    }
                 }
                 if (r == HIT) return HIT;
                 if (r == UNC) {

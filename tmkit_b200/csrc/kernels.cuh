@@ -107,9 +107,9 @@ template <typename T> __device__ __forceinline__ Vec3<T> bound_centre(const DGeo
 }
 
 /* narrowphase of two geometries with world poses */
-template <typename T, class UncTri = NoTri>
+template <typename T, class UncTri = NoTri, class NeedTri = NoTri>
 __device__ int test_geoms(const DGeom<T> &A, const Xf<T> &XA, const DGeom<T> &B, const Xf<T> &XB,
-                          const MeshRef<T> *meshes, UncTri on_unc_tri = UncTri()) {
+                          const MeshRef<T> *meshes, UncTri on_unc_tri = UncTri(), NeedTri on_need_tri = NeedTri()) {
     if (A.shape != K_MESH && B.shape != K_MESH) return test_convex(shape_of(A), XA, shape_of(B), XB);
     if (A.shape == K_MESH && B.shape == K_MESH) {
         if (!Num<T>::exact) return UNC;
@@ -150,8 +150,9 @@ __device__ int test_geoms(const DGeom<T> &A, const Xf<T> &XA, const DGeom<T> &B,
         }
         return SEP;
     }
-    if (A.shape == K_MESH) return test_mesh_shape(meshes[A.mesh], XA, shape_of(B), XB, B.brad, (unsigned *)nullptr, on_unc_tri);
-    return test_mesh_shape(meshes[B.mesh], XB, shape_of(A), XA, A.brad, (unsigned *)nullptr, on_unc_tri);
+    if (A.shape == K_MESH)
+        return test_mesh_shape(meshes[A.mesh], XA, shape_of(B), XB, B.brad, (unsigned *)nullptr, on_unc_tri, on_need_tri);
+    return test_mesh_shape(meshes[B.mesh], XB, shape_of(A), XA, A.brad, (unsigned *)nullptr, on_unc_tri, on_need_tri);
 }
 
 /* FK of the device joints + world poses of the moving geometries (thread-private arrays) */

@@ -89,9 +89,15 @@ struct UncList {
     uint32_t spill_cap;
     /* deferred mesh narrowphase: the pipeline exports its surviving mesh items (with the poses they need)
      * and k_heavy_items runs them with far more items in flight per SM than a phase of the tile loop can */
-    float4 *mesh_items; /* TMK_MESH_REC float4 per item */
+    float4 *mesh_items; /* TMK_MESH_REC float4 per item: mesh pairs */
     uint32_t *mesh_n;
     uint32_t mesh_cap;
+    float4 *conv_items; /* same records: convex pairs for SAT / GJK */
+    uint32_t *conv_n;
+    uint32_t conv_cap;
+    uint2 *tri_items;   /* (mesh record, triangle) the per-triangle certificates left open */
+    uint32_t *tri_n;
+    uint32_t tri_cap;
 };
 #define TMK_MESH_REC 5 /* float4 per exported mesh item: (id_x, id_y, key, -) poseA[7] - poseB[7] - */
 #define TMK_WHOLE_PAIR 0xffffffffu
@@ -102,6 +108,17 @@ __device__ __forceinline__ void unc_emit(const UncList &u, uint32_t id_x, uint32
 }
 /* mesh narrowphase hands its undecided TRIANGLES over one by one (the exact re-check of a whole
  * mesh pair in one thread is a long serial chain; single triangles are not) */
+struct TriNeed { /* k_mesh_traverse: open triangles go to the triangle list */
+    static constexpr bool enabled = true;
+    UncList u;
+    uint32_t rec;
+    uint32_t id_x, id_y, pair;
+    __device__ __forceinline__ void operator()(int tri) const {
+        const uint32_t i = atomicAdd(u.tri_n, 1u);
+        if (i < u.tri_cap) u.tri_items[i] = make_uint2(rec, (uint32_t)tri);
+        else unc_emit(u, id_x, id_y, pair, (uint32_t)tri); /* list full: decide the triangle exactly */
+    }
+};
 struct TriEmit {
     static constexpr bool enabled = true;
     UncList u;
@@ -519,7 +536,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         /* ---- X: export the heavy items - pairs the certificates left open (SAT / GJK) and mesh pairs (BVH
          * traversal) - of states that are still undecided.  As phases of this loop they were 60 % of the
          * tile time at 25 % of the instructions (few items, long dependent chains, everybody else waiting
-         * at the barrier); k_heavy_items runs them with thousands of items in flight per SM ---- */
+         * at the barrier); the wavefront kernels below run them with thousands of items in flight per SM ---- */
         {
             uint32_t total3 = 0;
 #pragma unroll
@@ -530,7 +547,8 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                 const uint32_t i = base + tid;
                 bool keep = false;
                 uint32_t e = 0;
-                if (i < total2) e = q2[i];
+                const bool conv = i < total2;
+                if (conv) e = q2[i];
                 else if (i < total) {
                     uint32_t off = i - total2;
                     int k = 0;
@@ -538,17 +556,20 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                     e = q3[(size_t)k * cfg.q3_cap + off];
                 }
                 if (i < total) keep = f_hit[ITEM_T(e)] == 0;
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                uint32_t dst = 0;
-                if (lane == 0 && m) dst = atomicAdd(unc.mesh_n, (uint32_t)__popc(m));
-                dst = __shfl_sync(0xffffffffu, dst, 0) + __popc(m & lt_mask);
+                const unsigned mc = __ballot_sync(0xffffffffu, keep && conv), mm = __ballot_sync(0xffffffffu, keep && !conv);
+                uint32_t dc = 0, dm = 0;
+                if (lane == 0 && mc) dc = atomicAdd(unc.conv_n, (uint32_t)__popc(mc));
+                if (lane == 0 && mm) dm = atomicAdd(unc.mesh_n, (uint32_t)__popc(mm));
+                dc = __shfl_sync(0xffffffffu, dc, 0) + __popc(mc & lt_mask);
+                dm = __shfl_sync(0xffffffffu, dm, 0) + __popc(mm & lt_mask);
                 if (keep) {
                     const int t = ITEM_T(e);
-                    if (dst < unc.mesh_cap) {
+                    const uint32_t dst = conv ? dc : dm;
+                    if (dst < (conv ? unc.conv_cap : unc.mesh_cap)) {
                         const Xf<float> XA = pose_at(ITEM_A(e), t);
                         Xf<float> XB = XA;
                         if (!ITEM_STATIC(e)) XB = pose_at(ITEM_B(e), t);
-                        float4 *rec = unc.mesh_items + (size_t)dst * TMK_MESH_REC;
+                        float4 *rec = (conv ? unc.conv_items : unc.mesh_items) + (size_t)dst * TMK_MESH_REC;
                         rec[0] = make_float4(__uint_as_float(unc_x[t]), __uint_as_float(unc_y[t]), __uint_as_float(ITEM_KEY(e)), 0.f);
                         rec[1] = make_float4(XA.r.x, XA.r.y, XA.r.z, XA.r.w);
                         rec[2] = make_float4(XA.v.x, XA.v.y, XA.v.z, XB.v.x);
@@ -567,36 +588,98 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     }
 }
 
-#ifndef HEAVY_MIN_CTAS
-#define HEAVY_MIN_CTAS 4
-#endif
-/* deferred narrowphase (SAT / GJK / mesh BVH): one thread per exported item */
+/* ------------------------------------------------------------------ deferred narrowphase, wavefront style:
+ * every kernel runs one kind of work with one item per thread, so that warps stay converged
+ * (as one mixed kernel only 3 of 32 lanes were active per instruction) */
+struct HeavyRec {
+    uint32_t id_x, id_y, key;
+    Xf<float> XA, XB;
+};
+__device__ __forceinline__ HeavyRec heavy_load(const float4 *rec) {
+    const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
+    HeavyRec h;
+    h.id_x = __float_as_uint(r0.x); h.id_y = __float_as_uint(r0.y); h.key = __float_as_uint(r0.z);
+    h.XA.r.x = r1.x; h.XA.r.y = r1.y; h.XA.r.z = r1.z; h.XA.r.w = r1.w;
+    h.XA.v.x = r2.x; h.XA.v.y = r2.y; h.XA.v.z = r2.z;
+    h.XB.r.x = r3.x; h.XB.r.y = r3.y; h.XB.r.z = r3.z; h.XB.r.w = r3.w;
+    h.XB.v.x = r2.w; h.XB.v.y = r4.x; h.XB.v.z = r4.y;
+    return h;
+}
+
+/* convex pairs the quick certificates left open: SAT / GJK */
 template <class Src, class Sink>
-__global__ void __launch_bounds__(128, HEAVY_MIN_CTAS) k_heavy_items(Image<float> im, Src src, Sink sink, UncList unc) {
+__global__ void __launch_bounds__(128) k_conv_items(Image<float> im, Src src, Sink sink, UncList unc) {
+    uint32_t n = *unc.conv_n;
+    if (n > unc.conv_cap) n = unc.conv_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const HeavyRec h = heavy_load(unc.conv_items + (size_t)i * TMK_MESH_REC);
+        const DGeom<float> &A = im.mg[ITEM_A(h.key)];
+        const DGeom<float> &B = ITEM_STATIC(h.key) ? im.sg[ITEM_B(h.key)] : im.mg[ITEM_B(h.key)];
+        const Xf<float> XB = ITEM_STATIC(h.key) ? xload(B.tf) : h.XB;
+        const int r = test_convex(shape_of(A), h.XA, shape_of(B), XB);
+        if (r == HIT) sink.mark_hit(src.from_id(h.id_x, h.id_y));
+        else if (r == UNC) unc_emit(unc, h.id_x, h.id_y, h.key, TMK_WHOLE_PAIR);
+    }
+}
+
+/* mesh pairs: AABB-tree traversal with the per-triangle certificates; open triangles go to the
+ * triangle list */
+template <class Src, class Sink>
+__global__ void __launch_bounds__(128) k_mesh_traverse(Image<float> im, Src src, Sink sink, UncList unc) {
     uint32_t n = *unc.mesh_n;
     if (n > unc.mesh_cap) n = unc.mesh_cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 *rec = unc.mesh_items + (size_t)i * TMK_MESH_REC;
-        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
-        const uint32_t id_x = __float_as_uint(r0.x), id_y = __float_as_uint(r0.y), key = __float_as_uint(r0.z);
-        Xf<float> XA, XB;
-        XA.r.x = r1.x; XA.r.y = r1.y; XA.r.z = r1.z; XA.r.w = r1.w;
-        XA.v.x = r2.x; XA.v.y = r2.y; XA.v.z = r2.z;
-        const DGeom<float> &A = im.mg[ITEM_A(key)];
-        const DGeom<float> *B;
-        if (ITEM_STATIC(key)) {
-            B = &im.sg[ITEM_B(key)];
-            XB = xload(B->tf);
-        } else {
-            B = &im.mg[ITEM_B(key)];
-            XB.r.x = r3.x; XB.r.y = r3.y; XB.r.z = r3.z; XB.r.w = r3.w;
-            XB.v.x = r2.w; XB.v.y = r4.x; XB.v.z = r4.y;
-        }
-        TriEmit on_tri;
-        on_tri.u = unc; on_tri.id_x = id_x; on_tri.id_y = id_y; on_tri.pair = key;
-        const int r = test_geoms(A, XA, *B, XB, im.meshes, on_tri);
-        if (r == HIT) sink.mark_hit(src.from_id(id_x, id_y));
-        else if (r == UNC) unc_emit(unc, id_x, id_y, key, TMK_WHOLE_PAIR);
+        const HeavyRec h = heavy_load(unc.mesh_items + (size_t)i * TMK_MESH_REC);
+        const DGeom<float> &A = im.mg[ITEM_A(h.key)];
+        const DGeom<float> &B = ITEM_STATIC(h.key) ? im.sg[ITEM_B(h.key)] : im.mg[ITEM_B(h.key)];
+        const Xf<float> XB = ITEM_STATIC(h.key) ? xload(B.tf) : h.XB;
+        TriEmit on_unc;
+        on_unc.u = unc; on_unc.id_x = h.id_x; on_unc.id_y = h.id_y; on_unc.pair = h.key;
+        TriNeed on_need;
+        on_need.u = unc; on_need.rec = i; on_need.id_x = h.id_x; on_need.id_y = h.id_y; on_need.pair = h.key;
+        const int r = test_geoms(A, h.XA, B, XB, im.meshes, on_unc, on_need);
+        if (r == HIT) sink.mark_hit(src.from_id(h.id_x, h.id_y));
+        else if (r == UNC) unc_emit(unc, h.id_x, h.id_y, h.key, TMK_WHOLE_PAIR);
+    }
+}
+
+/* both lists in one launch, triangles decided inline: for the swept-edge levels, whose lists are short
+ * and whose launch count matters more than warp convergence */
+template <class Src, class Sink>
+__global__ void __launch_bounds__(128) k_heavy_mixed(Image<float> im, Src src, Sink sink, UncList unc) {
+    uint32_t nc = *unc.conv_n, nm = *unc.mesh_n;
+    if (nc > unc.conv_cap) nc = unc.conv_cap;
+    if (nm > unc.mesh_cap) nm = unc.mesh_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nc + nm; i += gridDim.x * blockDim.x) {
+        const bool conv = i < nc;
+        const HeavyRec h = heavy_load((conv ? unc.conv_items : unc.mesh_items) + (size_t)(conv ? i : i - nc) * TMK_MESH_REC);
+        const DGeom<float> &A = im.mg[ITEM_A(h.key)];
+        const DGeom<float> &B = ITEM_STATIC(h.key) ? im.sg[ITEM_B(h.key)] : im.mg[ITEM_B(h.key)];
+        const Xf<float> XB = ITEM_STATIC(h.key) ? xload(B.tf) : h.XB;
+        TriEmit on_unc;
+        on_unc.u = unc; on_unc.id_x = h.id_x; on_unc.id_y = h.id_y; on_unc.pair = h.key;
+        const int r = test_geoms(A, h.XA, B, XB, im.meshes, on_unc);
+        if (r == HIT) sink.mark_hit(src.from_id(h.id_x, h.id_y));
+        else if (r == UNC) unc_emit(unc, h.id_x, h.id_y, h.key, TMK_WHOLE_PAIR);
+    }
+}
+
+/* one open triangle against the pair's convex shape: GJK */
+template <class Src, class Sink>
+__global__ void __launch_bounds__(128) k_tri_items(Image<float> im, Src src, Sink sink, UncList unc) {
+    uint32_t n = *unc.tri_n;
+    if (n > unc.tri_cap) n = unc.tri_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 it = unc.tri_items[i];
+        const HeavyRec h = heavy_load(unc.mesh_items + (size_t)it.x * TMK_MESH_REC);
+        const DGeom<float> &A = im.mg[ITEM_A(h.key)];
+        const DGeom<float> &B = ITEM_STATIC(h.key) ? im.sg[ITEM_B(h.key)] : im.mg[ITEM_B(h.key)];
+        const Xf<float> XB = ITEM_STATIC(h.key) ? xload(B.tf) : h.XB;
+        int r;
+        if (A.shape == K_MESH) r = test_mesh_tri_shape(im.meshes[A.mesh], h.XA, shape_of(B), XB, (int)it.y);
+        else r = test_mesh_tri_shape(im.meshes[B.mesh], XB, shape_of(A), h.XA, (int)it.y);
+        if (r == HIT) sink.mark_hit(src.from_id(h.id_x, h.id_y));
+        else if (r == UNC) unc_emit(unc, h.id_x, h.id_y, h.key, it.y);
     }
 }
 
