@@ -183,6 +183,7 @@ struct ImageDev {
     std::vector<double> q_base;
     uint64_t allow_serial = 0;
     bool valid = false;
+    uint64_t serial = 0; /* bumped whenever the image is rebuilt: cached CUDA graphs refer to its buffers */
     TileCfg wcfg, wcfg_e;
 };
 
@@ -215,6 +216,11 @@ struct aa_rx_cl {
     std::vector<uint8_t> last_pairhit;
     struct tmk_batch_stats stats;
     int use_tile; /* 1: tile-pipeline kernel (default), 0: thread-per-configuration kernel */
+    /* the swept-edge pipeline is ~45 short launches per batch: captured once per (arguments, buffers) into
+     * a CUDA graph and replayed, otherwise the host cannot enqueue as fast as the GPU executes */
+    struct EdgeGraph { uint64_t key[12]; cudaGraphExec_t exec; uint64_t used; size_t n_kernels; };
+    std::vector<EdgeGraph> edge_graphs;
+    uint64_t graph_clock = 0;
     UncList cur_unc;      /* undecided list of the batch in flight */
     cudaEvent_t *cur_ev;  /* its timing events (NULL when timing is off) */
 
@@ -334,6 +340,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
                     &cl->img.g_live};
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
+    for (auto &g : cl->edge_graphs) cudaGraphExecDestroy(g.exec);
     cudaFreeHost(cl->h_cnt);
     for (int k = 0; k < 8; k++) cudaEventDestroy(cl->ev_copy[k]);
     cudaStreamDestroy(cl->copy_stream);
@@ -757,6 +764,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     }
     if (mg.size() > 64) im.wcfg.smem = im.wcfg_e.smem = -1; /* queue items hold a 6-bit moving-geometry index */
     im.valid = true;
+    im.serial++;
 }
 
 /* ------------------------------------------------------------------ batch launches */
@@ -794,13 +802,12 @@ static void launch_heavy(const Image<float> &f, const Src &src, const Sink &sink
     CK(cudaGetLastError());
 }
 
-static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
+static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bool reset = true) {
     UncList u;
     u.cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states / 2), 0x7fffffffu);
     if (const char *e = getenv("TMK_UNC_CAP")) u.cap = (uint32_t)std::max(1, atoi(e)); /* test aid: forces k_overflow_all */
     cl->d_unc.need(sizeof(uint4) * (size_t)u.cap);
     cl->d_cnt.need(512);
-    CK(cudaMemsetAsync(cl->d_cnt.p, 0, 512, s));
     u.items = (uint4 *)cl->d_unc.p;
     u.n = (uint32_t *)cl->d_cnt.p;
     u.overflow = (uint32_t *)cl->d_cnt.p + 1;
@@ -827,6 +834,7 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s) {
     u.conv_n = (uint32_t *)cl->d_cnt.p + 5;
     u.tri_items = (uint2 *)cl->d_tri.p;
     u.tri_n = (uint32_t *)cl->d_cnt.p + 6;
+    if (reset) CK(cudaMemsetAsync(cl->d_cnt.p, 0, 512, s)); /* after every allocation: capturable */
     return u;
 }
 
@@ -903,14 +911,33 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
     const size_t small = getenv("TMK_EDGE_SMALL") ? (size_t)atol(getenv("TMK_EDGE_SMALL")) : 0; /* tuning aid */
     if (cl->use_tile && im.wcfg_e.smem > 0 && !st && n_edge >= small) {
-        /* fast path: bisection levels through the warp pipelines (pipeline.cuh) */
-        UncList u = unc_list(cl, n_edge * 4, s);
+        /* fast path: bisection levels through the tile pipeline (pipeline.cuh), replayed from a CUDA graph */
+        UncList u = unc_list(cl, n_edge * 4, s, false);
         if (n_edge == 0) return;
         const uint32_t ne = (uint32_t)n_edge;
         cl->d_nd.need(sizeof(int32_t) * n_edge);
         cl->d_efirst.need(sizeof(int32_t) * n_edge);
         cl->d_alive0.need(sizeof(uint32_t) * n_edge);
         cl->d_alive1.need(sizeof(uint32_t) * n_edge);
+        const bool use_graph = !cl->timing && !getenv("TMK_NO_GRAPH");
+        uint64_t key[12] = {(uint64_t)n_edge, (uint64_t)(uintptr_t)dQ0, (uint64_t)(uintptr_t)dQ1, (uint64_t)layout * 1315423911u + ld,
+                            0, (uint64_t)(uintptr_t)d_bits, (uint64_t)(uintptr_t)d_first, (uint64_t)(uintptr_t)s, im.serial,
+                            (uint64_t)(uintptr_t)cl->d_unc.p ^ ((uint64_t)(uintptr_t)cl->d_mesh.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_conv.p << 2),
+                            (uint64_t)(uintptr_t)cl->d_nd.p ^ ((uint64_t)(uintptr_t)cl->d_efirst.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_alive0.p << 2) ^
+                                ((uint64_t)(uintptr_t)cl->d_alive1.p << 3),
+                            (uint64_t)(uintptr_t)cl->d_spill.p ^ ((uint64_t)(uintptr_t)cl->d_tri.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_cnt.p << 2)};
+        memcpy(&key[4], &seg_len, sizeof(double));
+        if (use_graph) {
+            for (auto &g : cl->edge_graphs)
+                if (0 == memcmp(g.key, key, sizeof(key))) {
+                    g.used = ++cl->graph_clock;
+                    CK(cudaGraphLaunch(g.exec, s));
+                    cl->stats.n_launches += g.n_kernels; /* kernels run, not API calls */
+                    return;
+                }
+            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        }
+        CK(cudaMemsetAsync(cl->d_cnt.p, 0, 512, s));
         /* d_cnt: [0] undecided count, [1] overflow, [2..3] evaluated states, [8 + L] alive count of level L */
         uint32_t *cnt = (uint32_t *)cl->d_cnt.p;
         int32_t *nd = (int32_t *)cl->d_nd.p, *first = (int32_t *)cl->d_efirst.p;
@@ -953,6 +980,24 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         CK(cudaGetLastError());
         if (ev) CK(cudaEventRecord(ev[2], s));
         cl->stats.n_launches += launches + 3;
+        if (use_graph) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamEndCapture(s, &graph));
+            aa_rx_cl::EdgeGraph g;
+            memcpy(g.key, key, sizeof(key));
+            CK(cudaGraphInstantiate(&g.exec, graph, 0));
+            CK(cudaGraphDestroy(graph));
+            g.used = ++cl->graph_clock;
+            g.n_kernels = launches + 3;
+            if (cl->edge_graphs.size() >= 16) { /* replace the least recently used */
+                size_t lru = 0;
+                for (size_t k = 1; k < cl->edge_graphs.size(); k++)
+                    if (cl->edge_graphs[k].used < cl->edge_graphs[lru].used) lru = k;
+                cudaGraphExecDestroy(cl->edge_graphs[lru].exec);
+                cl->edge_graphs[lru] = g;
+            } else cl->edge_graphs.push_back(g);
+            CK(cudaGraphLaunch(g.exec, s));
+        }
         return;
     }
     /* instrumented path: one warp per edge */
