@@ -19,9 +19,10 @@
 #include "tmk_internal.h"
 
 #define MP_K 128        /* extensions proposed per iteration */
-#define MP_IK_SEEDS 48
+#define MP_IK_SEEDS 32
 #define MP_IK_ITERS 120
 #define MP_MAX_GOALS 16
+#define MP_IK_POLISH 8
 #define MP_MAX_BLOCKED 2048
 
 typedef struct {
@@ -308,7 +309,7 @@ int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
     /* lock-step iterations: one batched FK (GPU) per iteration for all candidates */
     size_t n_done = 0;
     /* stop early once plenty of candidates have converged and the stragglers had their chance */
-    for (int it = 0; it < MP_IK_ITERS && n_done < S && !(n_done >= 12 && it >= 24); it++) {
+    for (int it = 0; it < MP_IK_ITERS && n_done < S && !(n_done >= 8 && it >= 16); it++) {
         aa_rx_sg_tf_batch(mp->sg, S, n, mp->ids, mp->n_all, mp->q_start_all, Q, n, n_fr, frames, TF);
         mp->st.n_ik_iterations++;
         for (size_t s = 0; s < S; s++) {
@@ -332,8 +333,23 @@ int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
     double cand[MP_IK_SEEDS][TMK_MP_MAXSUB];
     double cand_cost[MP_IK_SEEDS];
     size_t n_cand = 0;
-    for (size_t s = 0; s < S; s++) {
-        if (!done[s]) continue;
+    /* nearest to the start first; the double-precision polish is a GPU round trip per iteration, so only
+     * the MP_IK_POLISH most promising candidates get it */
+    size_t order[MP_IK_SEEDS], n_ord = 0;
+    double ocost[MP_IK_SEEDS];
+    {
+        double start_sub[TMK_MP_MAXSUB];
+        for (size_t k = 0; k < n; k++) start_sub[k] = mp->q_start_all[mp->ids[k]];
+        for (size_t s = 0; s < S; s++) {
+            if (!done[s]) continue;
+            double c = dist(Q + s * n, start_sub, n);
+            size_t pos = n_ord++;
+            while (pos > 0 && ocost[pos - 1] > c) { order[pos] = order[pos - 1]; ocost[pos] = ocost[pos - 1]; pos--; }
+            order[pos] = s; ocost[pos] = c;
+        }
+    }
+    for (size_t oi = 0; oi < n_ord && oi < MP_IK_POLISH; oi++) {
+        const size_t s = order[oi];
         double *q = Q + s * n;
         double ep = 1, eo = 1;
         for (int it = 0; it < 6; it++) {
