@@ -569,7 +569,6 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         }
         return dist > reach * (1 + 1e-9) + 1e-4;
     };
-    size_t n_unreachable = 0;
 
     struct P { uint32_t w; int fa, fb, owner, seg; };
     std::vector<P> pairs;
@@ -580,7 +579,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
             if (g2m[b] >= 0 && g2m[b] > g2m[a]) continue; /* owned by b */
             int fa = cl->geoms[a].frame, fb = cl->geoms[b].frame;
             if (!pair_live(cl, fa, fb)) continue;
-            if (g2m[b] < 0 && unreachable(mg[g2m[a]], sgv[g2s[b]])) { n_unreachable++; continue; }
+            if (g2m[b] < 0 && unreachable(mg[g2m[a]], sgv[g2s[b]])) continue;
             int cls = pair_class(cl->geoms[a].shape, cl->geoms[b].shape);
             P p;
             p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls, cl->geoms[b].shape)

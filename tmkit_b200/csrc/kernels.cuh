@@ -1,14 +1,15 @@
-/* kernels.cuh - device tables and kernels of the validity check (sm_100a).
- *
- * Kernels (SURVEY.md 7 / BASELINE.json north_star numbering):
- *   k_fk_batch       K1  one thread per configuration, FK over the frame table, writes TF_abs
- *   k_check_cfg<T>       reference-shaped path: one thread per configuration, FK + all pairs
- *                        inline.  T=double is the exact re-check of uncertain configurations
- *                        and the engine of the single-configuration ABI.
- *   k_validity_tile  K1+K2+K3 fused per tile of configurations: FK -> poses in shared memory,
- *                        warp-cooperative broadphase with ballot compaction into a shared
- *                        queue, narrowphase one thread per surviving pair (tile.cuh)
- *   k_check_edges    K4  one warp per edge, 32 interior states per round in OMPL order
+/* kernels.cuh - device tables shared by all kernels, and the kernels that are NOT the batch pipeline
+ * (that one lives in pipeline.cuh):
+ *   k_fk_batch            K1 standalone (aa_rx_sg_tf_batch): one thread per configuration, FP32 chain over
+ *                         the full frame table staged in shared memory, writes the requested frames
+ *   k_fk_single64         aa_rx_sg_tf: one configuration, double
+ *   k_pairs_tf64          aa_rx_cl_check / allow_config / hoisted static pairs: one thread per geometry
+ *                         pair on caller-provided absolute transforms, double
+ *   k_check_cfg<T, LIST>  one thread per configuration, FK + all pairs inline: the instrumented path
+ *                         (statistics, :track-collisions pair flags), the fallback for images the tile
+ *                         kernel cannot hold, and (T = double, LIST) its exact re-check
+ *   k_check_edges<T>,     one warp per edge / one thread per listed edge: the instrumented swept-edge
+ *   k_recheck_edges64     path
  */
 #pragma once
 #include "dev_math.cuh"
