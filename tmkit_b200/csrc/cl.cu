@@ -585,7 +585,10 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
             p.w = g2m[b] >= 0 ? pair_pack(g2m[a], g2m[b], 0, cls, cl->geoms[b].shape)
                               : pair_pack(g2m[a], g2s[b], 1, cls, cl->geoms[b].shape);
             p.fa = fa; p.fb = fb; p.owner = g2m[a];
-            p.seg = g2m[b] >= 0 ? 2 : ((cl->geoms[b].shape == TMK_BOX || cl->geoms[b].shape == TMK_MESH) ? 1 : 0);
+            /* segment 1 (exact sphere-to-oriented-box distance, 2x the cost of a sphere test) pays off for
+             * large flat boxes and mesh boxes; a small box is as well served by its bounding sphere */
+            const bool big_box = (cl->geoms[b].shape == TMK_BOX && cl->geoms[b].brad > 0.2) || cl->geoms[b].shape == TMK_MESH;
+            p.seg = g2m[b] >= 0 ? 2 : (big_box ? 1 : 0);
             pairs.push_back(p);
         }
     }
@@ -655,6 +658,12 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     std::vector<uint32_t> h_tpairs;
     for (auto &p : tpairs) h_tpairs.push_back(p.w);
     std::vector<int> pa_begin(3 * mg.size() + 1, 0);
+    if (getenv("TMK_DEBUG_IMAGE")) {
+        size_t seg_n[3] = {0, 0, 0};
+        for (auto &p : tpairs) seg_n[p.seg]++;
+        fprintf(stderr, "tmkcl image: %zu joints, %zu moving / %zu static geometries, %zu pairs (%zu in the pipeline list: %zu sphere, %zu box, %zu moving), grid %s (%zu obstacles)\n",
+                joints.size(), mg.size(), sgv.size(), pairs.size(), tpairs.size(), seg_n[0], seg_n[1], seg_n[2], grid_on ? "on" : "off", grid_on ? n_gridded : (size_t)0);
+    }
     for (auto &p : tpairs) pa_begin[3 * p.owner + p.seg + 1]++;
     for (size_t k = 0; k < 3 * mg.size(); k++) pa_begin[k + 1] += pa_begin[k];
 
