@@ -66,7 +66,23 @@ TMK_HD float t_max(float a, float b) { return fmaxf(a, b); }
 TMK_HD double t_max(double a, double b) { return fmax(a, b); }
 TMK_HD float t_min(float a, float b) { return fminf(a, b); }
 TMK_HD double t_min(double a, double b) { return fmin(a, b); }
-TMK_HD void t_sincos(float a, float *s, float *c) { sincosf(a, s, c); }
+/* sin / cos of a joint half-angle: Cody-Waite reduction by pi/2 and the classic minimax polynomials on
+ * [-pi/4, pi/4] - about 1e-7 absolute for |a| < 100, a third of the instructions of sincosf (whose
+ * large-argument path is never needed here).  Larger arguments fall back to sincosf. */
+TMK_HD void t_sincos(float a, float *s, float *c) {
+    if (!(fabsf(a) < 100.0f)) { sincosf(a, s, c); return; }
+    const float k = rintf(a * 0.636619772367581343f);
+    float r = fmaf(-k, 1.57079637050628662109375f, a);  /* float(pi/2) ... */
+    r = fmaf(-k, -4.37113882867379e-8f, r);            /* ... and the rest of pi/2 */
+    const float r2 = r * r;
+    const float sn = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+    const float cs = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                          fmaf(-0.5f, r2, 1.0f));
+    const int q = (int)k;
+    const float s0 = (q & 1) ? cs : sn, c0 = (q & 1) ? sn : cs;
+    *s = (q & 2) ? -s0 : s0;
+    *c = ((q + 1) & 2) ? -c0 : c0;
+}
 TMK_HD void t_sincos(double a, double *s, double *c) { sincos(a, s, c); }
 
 /* ------------------------------------------------------------------ vectors, quaternions, poses */
@@ -148,9 +164,16 @@ TMK_HD Xf<T> fk_joint(const Xf<T> &E, Vec3<T> axis, T offset, int type, T q, con
     if (type == 1) {
         T s, c;
         t_sincos(T(0.5) * a, &s, &c);
-        Quat<T> qa;
-        qa.x = axis.x * s; qa.y = axis.y * s; qa.z = axis.z * s; qa.w = c;
-        rel.r = qmul(E.r, qa);
+        if (axis.x == T(0) && axis.y == T(0) && axis.z == T(1)) { /* URDF-style joints: half the multiplies */
+            rel.r.x = E.r.x * c + E.r.y * s;
+            rel.r.y = E.r.y * c - E.r.x * s;
+            rel.r.z = E.r.z * c + E.r.w * s;
+            rel.r.w = E.r.w * c - E.r.z * s;
+        } else {
+            Quat<T> qa;
+            qa.x = axis.x * s; qa.y = axis.y * s; qa.z = axis.z * s; qa.w = c;
+            rel.r = qmul(E.r, qa);
+        }
         rel.v = E.v;
     } else {
         rel.r = E.r;
