@@ -494,6 +494,67 @@ def test_static_grid_equals_brute_force(monkeypatch):
     _assert_verdicts(v_grid[:1500], st, "clutter with a grid")
 
 
+def test_branching_joint_tree():
+    """a lift joint carrying two short arms, all varied: the second arm's first joint does not follow its
+    parent directly in the joint list, so its parent pose comes from the joint-pose slab."""
+    sc = S.Scene()
+    sc.add(S.Frame("floor", "", S.FIXED, geoms=[S.Geom(S.BOX, (2.0, 2.0, 0.02))]))
+    sc.add(S.Frame("lift", "", S.PRISMATIC, (0, 0, 0, 1), (0, 0, 0.3), (0, 0, 1.0), "lift", 0.0, (0.0, 0.6),
+                   geoms=[S.Geom(S.BOX, (0.2, 0.3, 0.2))]))
+    for side, y in (("r", -0.2), ("l", 0.2)):
+        sc.add(S.Frame(f"{side}0", "lift", S.REVOLUTE, S.quat_from_rpy(0, 0, 0), (0, y, 0.0), (0, 1.0, 0), f"{side}0", 0.0, (-2.5, 2.5)))
+        sc.add(S.Frame(f"{side}0c", f"{side}0", S.FIXED, S.quat_from_rpy(0, 1.5708, 0), (0.0, 0, 0), geoms=[S.Geom(S.CYLINDER, (0.3, 0.04, 0))]))
+        sc.add(S.Frame(f"{side}1", f"{side}0", S.REVOLUTE, (0, 0, 0, 1), (0.3, 0, 0), (0, 0, 1.0), f"{side}1", 0.0, (-2.5, 2.5)))
+        sc.add(S.Frame(f"{side}1c", f"{side}1", S.FIXED, S.quat_from_rpy(0, 1.5708, 0), (0.0, 0, 0), geoms=[S.Geom(S.CYLINDER, (0.25, 0.03, 0))]))
+        sc.add(S.Frame(f"{side}tip", f"{side}1", S.FIXED, (0, 0, 0, 1), (0.27, 0, 0), geoms=[S.Geom(S.SPHERE, (0.05, 0, 0))]))
+    sc.add(S.Frame("post", "", S.FIXED, (0, 0, 0, 1), (0.35, 0.0, 0.5), geoms=[S.Geom(S.CYLINDER, (0.6, 0.05, 0))]))
+    sc.allowed = [("lift", "r0c"), ("lift", "l0c"), ("r0c", "r1c"), ("l0c", "l1c"), ("r1c", "rtip"), ("l1c", "ltip")]
+    names = ["lift", "r0", "r1", "l0", "l1"]
+    sg = A.SceneGraph.from_scene(sc)
+    cl = A.Collision(sg)
+    orc = O.OracleScene(S.flatten(sc))
+    q0 = np.zeros(5)
+    sub = sg.config_indices(names)
+    lim = np.asarray([[0.0, 0.6], [-2.5, 2.5], [-2.5, 2.5], [-2.5, 2.5], [-2.5, 2.5]])
+    Q = W.random_configs(lim, 8000, seed=3)
+    valid = cl.check_batch(sub, q0, Q)
+    st, _ = orc.check_batch(orc.config_ids(names), q0, Q, threads=CORES)
+    _assert_verdicts(valid, st, "branching tree")
+    assert 0.05 < valid.mean() < 0.95
+    a, b = W.random_configs(lim, 600, seed=4), W.random_configs(lim, 600, seed=5)
+    seg = 0.01 * float(np.linalg.norm(lim[:, 1] - lim[:, 0]))
+    ev, first = cl.check_edges(sub, q0, a, b, seg)
+    est, _, ofirst, _ = orc.check_edges(orc.config_ids(names), q0, a, b, seg, threads=CORES)
+    _assert_verdicts(ev, est, "branching tree edges", max_band_frac=0.05)
+    out = sg.tf_batch(sub, q0, Q[:50])
+    for c in range(50):
+        q = q0.copy()
+        q[orc.config_ids(names)] = Q[c]
+        ok, err = tf_close(out[c], orc.fk(q)[1], FK_RTOL)
+        assert ok, (c, err)
+
+
+def test_fk_batch_in_a_scene_with_hundreds_of_frames():
+    """aa_rx_sg_tf_batch evaluates only the requested frames and their ancestors."""
+    sc = S.clutter_scene(512, seed=0)
+    sg = A.SceneGraph.from_scene(sc)
+    orc = O.OracleScene(S.flatten(sc))
+    q0 = S.q0_vector(sc)
+    sub = sg.config_indices(S.RIGHT_ARM)
+    Q = W.random_configs(W.arm_limit_table(S.RIGHT_ARM), 40, seed=1)
+    frames = [sg.frame_id("right_endpoint"), sg.frame_id("obstacle_17"), sg.frame_id("right_e1")]
+    out = sg.tf_batch(sub, q0, Q, frames=frames)
+    for c in range(40):
+        q = sg.config_set(sub, Q[c], q0)
+        ab = orc.fk(q)[1]
+        ok, err = tf_close(out[c], ab[frames], FK_RTOL)
+        assert ok, (c, err)
+    full = sg.tf_batch(sub, q0, Q[:4])  # all 570 frames: the slab shrinks its thread count to fit
+    assert full.shape == (4, sg.frame_count(), 7)
+    ok, err = tf_close(full[0], orc.fk(sg.config_set(sub, Q[0], q0))[1], FK_RTOL)
+    assert ok, err
+
+
 def test_prismatic_and_sphere_scene():
     """a hand-built scene with a prismatic joint, spheres and a static mesh."""
     sc = S.Scene()

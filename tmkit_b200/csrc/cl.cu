@@ -1282,17 +1282,39 @@ extern "C" void aa_rx_sg_tf_batch(const struct aa_rx_sg *sg, size_t n_cfg, size_
             fr[frames[k]].out = (int)k;
         }
     if (n_cfg == 0 || n_out == 0) return;
-    const int T = 64;
-    size_t smem = ((sizeof(FFrame) * n_f + 15) & ~(size_t)15) + sizeof(float) * 7 * n_f * T;
-    if (smem > 200 * 1024) tmk_die("aa_rx_sg_tf_batch: %zu frames exceed the shared-memory slab", n_f);
+    /* only the requested frames and their ancestors are evaluated (an IK chain in a scene with hundreds of
+     * obstacle frames is still ~20 frames) */
+    std::vector<char> need(n_f, frames ? 0 : 1);
+    if (frames)
+        for (size_t i = n_f; i-- > 0;) {
+            if (fr[i].out >= 0) need[i] = 1;
+            if (need[i] && fr[i].parent >= 0) need[fr[i].parent] = 1;
+        }
+    std::vector<int> remap(n_f, -1);
+    std::vector<FFrame> sel;
+    for (size_t i = 0; i < n_f; i++)
+        if (need[i]) {
+            remap[i] = (int)sel.size();
+            FFrame F = fr[i];
+            if (F.parent >= 0) F.parent = remap[F.parent]; /* parents precede children */
+            sel.push_back(F);
+        }
+    const size_t n_sel = sel.size();
+    int T = 64;
+    size_t smem = 0;
+    for (;; T /= 2) {
+        smem = ((sizeof(FFrame) * n_sel + 15) & ~(size_t)15) + sizeof(float) * 7 * n_sel * (size_t)T;
+        if (smem <= 200 * 1024) break;
+        if (T == 8) tmk_die("aa_rx_sg_tf_batch: %zu frames exceed the shared-memory slab", n_sel);
+    }
     SgDev *sd = sg_dev(sg);
     DBuf &dfr = sd->b_frames, &dq = sd->b_q, &dout = sd->b_out;
-    upload(dfr, fr, 0);
+    upload(dfr, sel, 0);
     dq.need(n_cfg * ldQ * 8);
     CK(cudaMemcpyAsync(dq.p, Q_sub, n_cfg * ldQ * 8, cudaMemcpyHostToDevice, 0));
     dout.need(n_cfg * n_out * 7 * 8);
-    CK(cudaFuncSetAttribute(k_fk_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fk_batch<<<(unsigned)((n_cfg + T - 1) / T), T, smem>>>((const FFrame *)dfr.p, (int)n_f, (const double *)dq.p, ldQ,
+    CK(cudaFuncSetAttribute(k_fk_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_fk_batch<<<(unsigned)((n_cfg + T - 1) / T), T, smem>>>((const FFrame *)dfr.p, (int)n_sel, (const double *)dq.p, ldQ,
                                                              n_cfg, (int)n_out, (double *)dout.p);
     CK(cudaGetLastError());
     CK(cudaMemcpy(TF_abs_out, dout.p, n_cfg * n_out * 7 * 8, cudaMemcpyDeviceToHost));
