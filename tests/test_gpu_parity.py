@@ -555,6 +555,92 @@ def test_fk_batch_in_a_scene_with_hundreds_of_frames():
     assert ok, err
 
 
+def _random_scene(rng):
+    """a random articulated tree (2-6 joints, arbitrary axes and offsets, revolute and prismatic, every
+    primitive kind incl. a moving mesh now and then) among random static obstacles incl. a mesh."""
+    sc = S.Scene()
+    sc.add(S.Frame("base", "", S.FIXED, _rand_quat(rng), tuple(rng.uniform(-0.2, 0.2, 3))))
+    n_j = int(rng.integers(2, 7))
+    names, lims, links = [], [], ["base"]
+    for j in range(n_j):
+        parent = links[int(rng.integers(max(0, len(links) - 2), len(links)))]  # mostly a chain, sometimes a branch
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        prismatic = rng.random() < 0.25
+        lim = (-0.3, 0.3) if prismatic else (-2.8, 2.8)
+        name = f"j{j}"
+        sc.add(S.Frame(name, parent, S.PRISMATIC if prismatic else S.REVOLUTE, _rand_quat(rng), tuple(rng.uniform(-0.25, 0.25, 3)),
+                       tuple(ax), name, float(rng.uniform(-0.3, 0.3)), lim))
+        kind = rng.random()
+        if kind < 0.35:
+            g = S.Geom(S.BOX, tuple(rng.uniform(0.04, 0.25, 3)))
+        elif kind < 0.7:
+            g = S.Geom(S.CYLINDER, (float(rng.uniform(0.08, 0.3)), float(rng.uniform(0.02, 0.07)), 0.0))
+        elif kind < 0.92:
+            g = S.Geom(S.SPHERE, (float(rng.uniform(0.03, 0.09)), 0, 0))
+        else:
+            v, t = S._grid_box_mesh(tuple(rng.uniform(0.03, 0.1, 3)), (0, 0, 0), 2)
+            g = S.Geom(S.MESH, (0, 0, 0), v, t)
+        sc.add(S.Frame(f"{name}_g", name, S.FIXED, _rand_quat(rng), tuple(rng.uniform(-0.1, 0.1, 3)), geoms=[g]))
+        sc.allowed.append((f"{parent}_g" if parent != "base" else "base", f"{name}_g"))
+        names.append(name)
+        lims.append(lim)
+        links.append(name)
+    sc.allowed = [(a, b) for a, b in sc.allowed if a != "base"]
+    for k in range(int(rng.integers(4, 14))):
+        c = tuple(rng.uniform(-0.8, 0.8, 3))
+        kind = rng.random()
+        if kind < 0.4:
+            g = S.Geom(S.BOX, tuple(rng.uniform(0.03, 0.6, 3)))
+        elif kind < 0.7:
+            g = S.Geom(S.CYLINDER, (float(rng.uniform(0.05, 0.5)), float(rng.uniform(0.02, 0.12)), 0.0))
+        elif kind < 0.9:
+            g = S.Geom(S.SPHERE, (float(rng.uniform(0.03, 0.2)), 0, 0))
+        else:
+            v, t = S._tube_mesh(float(rng.uniform(0.05, 0.2)), float(rng.uniform(0.03, 0.15)), -0.2, 0.2, 8, 2)
+            g = S.Geom(S.MESH, (0, 0, 0), v, t)
+        sc.add(S.Frame(f"obs{k}", "", S.FIXED, _rand_quat(rng), c, geoms=[g]))
+    return sc, names, np.asarray(lims, dtype=np.float64)
+
+
+def _rand_quat(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return tuple(float(x) for x in q)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scenes_fuzz(seed):
+    """generic parity: random trees, axes, joint kinds, shapes, meshes - configurations and edges."""
+    rng = np.random.default_rng(1000 + seed)
+    sc, names, lim = _random_scene(rng)
+    sg = A.SceneGraph.from_scene(sc)
+    orc = O.OracleScene(S.flatten(sc))
+    q0 = np.zeros(len(orc.config_names))
+    sg.allow_config(q0)
+    orc.allow_config(q0)
+    cl = A.Collision(sg)
+    sub = sg.config_indices(names)
+    osub = orc.config_ids(names)
+    Q = W.random_configs(lim, 1500, seed=seed)
+    valid = cl.check_batch(sub, q0, Q)
+    st, _ = orc.check_batch(osub, q0, Q, threads=CORES)
+    _assert_verdicts(valid, st, f"random scene {seed}", max_band_frac=0.03)
+    a, b = W.random_configs(lim, 150, seed=seed + 50), W.random_configs(lim, 150, seed=seed + 90)
+    seg = 0.01 * float(np.linalg.norm(lim[:, 1] - lim[:, 0]))
+    ev, first = cl.check_edges(sub, q0, a, b, seg)
+    est, _, ofirst, _ = orc.check_edges(osub, q0, a, b, seg, threads=CORES)
+    _assert_verdicts(ev, est, f"random scene {seed} edges", max_band_frac=0.08)
+    sure = (est != O.BAND) & (ofirst != -2)
+    assert np.array_equal(first[sure], ofirst[sure])
+    out = sg.tf_batch(sub, q0, Q[:20])
+    for c in range(20):
+        q = q0.copy()
+        q[osub] = Q[c]
+        ok, err = tf_close(out[c], orc.fk(q)[1], FK_RTOL)
+        assert ok, (seed, c, err)
+
+
 def test_prismatic_and_sphere_scene():
     """a hand-built scene with a prismatic joint, spheres and a static mesh."""
     sc = S.Scene()
