@@ -143,3 +143,43 @@ def test_collision_feedback(built):
         assert any(n.startswith("right_") for n in names)
         return
     pytest.fail("every sampled goal was directly reachable")
+
+
+def test_c_executor_replays_the_plan(built, tmp_path):
+    """the whole boundary in C: a scene plugin generated as C source (what the reference's aarxc emits,
+    Makefile.am:213-231), loaded with aa_rx_dl_sg, the start file and the plan file read with
+    tmk_plan_parse, every waypoint checked with aa_rx_sg_tf + aa_rx_cl_check exactly as
+    demo/tmpexec.c:362-428 does, the segments through aa_rx_cl_check_edges at the planner's resolution, reparents applied
+    with aa_rx_sg_rel_tf / _copy / _reparent_name / _init (tmpexec.c:307-348)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "harness", "plan_check")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tests", "harness"), "plan_check"])
+    sc = S.baxter_sussman()
+    src = tmp_path / "sussman_scene.c"
+    src.write_text(S.to_plugin_source(sc, "sussman"))
+    so = tmp_path / "libsussman_scene.so"
+    libdir = os.path.join(root, "tmkit_b200")
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", f"-I{root}/include", "-o", str(so), str(src), f"-L{libdir}",
+                           "-l:libtmkcl.so", f"-Wl,-rpath,{libdir}"])
+    r = SU.run(seed=3)
+    assert r.ok
+    plan_file = tmp_path / "plan.tmp"
+    assert r.plan.write(str(plan_file)) == 0
+    start = A.PlanFile()
+    q0 = S.q0_vector(sc)
+    start.add_motion(sc.config_names(), q0[None, :])
+    start_file = tmp_path / "q0.tmp"
+    assert start.write(str(start_file)) == 0
+    p = subprocess.run([exe, str(so), "sussman", str(start_file), str(plan_file), "0.01"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.strip().splitlines()
+    assert sum(l.startswith("motion") for l in lines) == 6 and sum(l.startswith("reparent") for l in lines) == 6
+    assert lines[-1].startswith("summary  6 motions, 6 reparents") and lines[-1].endswith(" 0 colliding")
+    final = {l.split()[1]: np.array(l.split()[2:], dtype=float) for l in lines if l.startswith("final")}
+    # the C executor, starting from the plugin's scene, ends with the same stack the Python driver built
+    orc = O.OracleScene(S.flatten(r.scene_final))
+    ab = orc.fk(r.q_final)[1]
+    for name, pos in final.items():
+        np.testing.assert_allclose(pos, ab[orc.frame_id(name)][4:], atol=1e-8)
+    assert final["block_a"][2] - final["block_b"][2] == pytest.approx(0.1001, abs=1e-6)

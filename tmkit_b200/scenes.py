@@ -498,3 +498,65 @@ def flatten(sc: Scene) -> Dict[str, np.ndarray]:
         allowed[i, j] = allowed[j, i] = 1
     out["allowed"] = allowed
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Scene plugin source (what the reference's `aarxc` emits: Makefile.am:213-231)
+# --------------------------------------------------------------------------------------
+
+def to_plugin_source(sc: Scene, scene_name: str) -> str:
+    """C source of a scene plugin: one constructor ``aa_rx_dl_sg__<scene_name>`` that feeds the scene
+    through the ingest ABI (aa_rx_sg_add_frame_*, aa_rx_geom_*, aa_rx_geom_attach,
+    aa_rx_sg_allow_collision_name).  Compile with ``gcc -shared -fPIC -I include`` and load it with
+    aa_rx_dl_sg (demo/tmpexec.c:172)."""
+    def arr(xs, fmt="%.17g", suffix=""):
+        def lit(x):
+            t = fmt % float(x)
+            if "." not in t and "e" not in t and "n" not in t:
+                t += ".0"  # "0f" is not a C literal
+            return t + suffix
+        return "{" + ", ".join(lit(x) for x in xs) + "}"
+
+    out = ['#include "tmkit_b200/amino_rx.h"', ""]
+    mesh_id = 0
+    body = []
+    for f in sc.frames:
+        body.append("    {")
+        body.append(f"        static const double q[4] = {arr(f.quat)}, v[3] = {arr(f.xyz)}, ax[3] = {arr(f.axis)};")
+        if f.type == FIXED:
+            body.append(f'        aa_rx_sg_add_frame_fixed(sg, "{f.parent}", "{f.name}", q, v);')
+            body.append("        (void)ax;")
+        else:
+            fn = "aa_rx_sg_add_frame_revolute" if f.type == REVOLUTE else "aa_rx_sg_add_frame_prismatic"
+            body.append(f'        {fn}(sg, "{f.parent}", "{f.name}", q, v, "{f.config}", ax, {float(f.offset):.17g});')
+            if f.limits is not None:
+                body.append(f'        aa_rx_sg_set_limit_pos(sg, "{f.config}", {float(f.limits[0]):.17g}, {float(f.limits[1]):.17g});')
+        for g in f.geoms:
+            if g.shape == BOX:
+                body.append(f"        {{ static const double d[3] = {arr(g.dims)}; aa_rx_geom_attach(sg, \"{f.name}\", aa_rx_geom_box(0, d)); }}")
+            elif g.shape == SPHERE:
+                body.append(f'        aa_rx_geom_attach(sg, "{f.name}", aa_rx_geom_sphere(0, {float(g.dims[0]):.17g}));')
+            elif g.shape == CYLINDER:
+                body.append(f'        aa_rx_geom_attach(sg, "{f.name}", aa_rx_geom_cylinder(0, {float(g.dims[0]):.17g}, {float(g.dims[1]):.17g}));')
+            else:
+                vv = np.asarray(g.verts, dtype=np.float32).reshape(-1)
+                ii = np.asarray(g.tris, dtype=np.uint32).reshape(-1)
+                out.append(f"static const float mesh{mesh_id}_v[] = {arr(vv, '%.9g', 'f')};")
+                out.append(f"static const unsigned mesh{mesh_id}_i[] = {{{', '.join(str(int(x)) for x in ii)}}};")
+                body.append("        {")
+                body.append("            struct aa_rx_mesh *m = aa_rx_mesh_create();")
+                body.append(f"            aa_rx_mesh_set_vertices(m, {len(vv) // 3}, mesh{mesh_id}_v, 0);")
+                body.append(f"            aa_rx_mesh_set_indices(m, {len(ii) // 3}, mesh{mesh_id}_i, 0);")
+                body.append(f'            aa_rx_geom_attach(sg, "{f.name}", aa_rx_geom_mesh(0, m));')
+                body.append("            aa_rx_mesh_destroy(m);")
+                body.append("        }")
+                mesh_id += 1
+        body.append("    }")
+    for a, b in sc.allowed:
+        body.append(f'    aa_rx_sg_allow_collision_name(sg, "{a}", "{b}", 1);')
+    out.append("")
+    out.append(f"struct aa_rx_sg *aa_rx_dl_sg__{scene_name}(struct aa_rx_sg *sg) {{")
+    out.extend(body)
+    out.append("    return sg;")
+    out.append("}")
+    return "\n".join(out) + "\n"
