@@ -472,7 +472,8 @@ def main():
     fp32_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     flops_unit = f_cfg * states_per_unit
     achieved_tf = flops_unit * n_units / (k_ms * 1e-3) / 1e12
-    kernel = "k_states_tile<SrcEdgeLevel> (all bisection levels)" if edges else "k_states_tile<SrcConfigs>"
+    kernel = ("k_states_tile<SrcEdgeLevel> + k_heavy_mixed + k_edges_compact, all bisection levels" if edges
+              else "k_states_tile<SrcConfigs> + deferred narrowphase (k_conv_items, k_mesh_traverse, k_tri_items)")
 
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
