@@ -960,15 +960,24 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         uint32_t *alive[2] = {(uint32_t *)cl->d_alive0.p, (uint32_t *)cl->d_alive1.p};
         const uint32_t *cur_alive = nullptr, *cur_n = nullptr;
         size_t launches = 1;
+        /* heavy items (GJK, mesh traversals) of several levels are collected and run in one launch: a short
+         * dependent kernel costs its latency, not its work, and a position decided late still merges
+         * through atomicMin - the price is the few edges that bisect one level further than needed */
+        const unsigned hmask = getenv("TMK_EDGE_HEAVY_MASK") ? (unsigned)strtoul(getenv("TMK_EDGE_HEAVY_MASK"), nullptr, 0) : 0x2222u;
+        int group0 = 0;
         for (int L = 0; L < TMK_EDGE_LEVELS; L++) {
             src.alive = cur_alive; src.n_alive = cur_n; src.level = L;
-            u.mesh_n = cnt + 32 + L; u.conv_n = cnt + 48 + L; u.tri_n = cnt + 64 + L;
+            u.mesh_n = cnt + 32 + group0; u.conv_n = cnt + 48 + group0; u.tri_n = cnt + 64 + group0;
             launch_tile<SrcEdgeLevel, SinkEdgeFirst>(im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2),
                                                      (unsigned)im.wcfg_e.grid, s);
             CK(cudaGetLastError());
-            k_heavy_mixed<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
-            CK(cudaGetLastError());
-            launches += 2;
+            launches++;
+            if (((hmask >> L) & 1) || L + 1 == TMK_EDGE_LEVELS) {
+                k_heavy_mixed<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
+                CK(cudaGetLastError());
+                launches++;
+                group0 = L + 1;
+            }
             if (L + 1 < TMK_EDGE_LEVELS) {
                 uint32_t *out = alive[L & 1], *n_out = cnt + 8 + L;
                 k_edges_compact<<<148 * 2, 256, 0, s>>>(cur_alive, cur_n, ne, nd, first, L, out, n_out);
