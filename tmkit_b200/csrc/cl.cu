@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <mutex>
 #include <vector>
 
 #include "kernels.cuh"
@@ -29,18 +31,126 @@ using namespace tmk;
                     __LINE__, cudaGetErrorString(e_));                                               \
     } while (0)
 
+/* host-side spans to stderr when TMK_PROFILE_HOST is set (tuning aid) */
+struct HostSpan {
+    static bool on() { static int v = -1; if (v < 0) v = getenv("TMK_PROFILE_HOST") ? 1 : 0; return v == 1; }
+    std::chrono::steady_clock::time_point t0;
+    const char *what;
+    explicit HostSpan(const char *w) : what(w) { if (on()) t0 = std::chrono::steady_clock::now(); }
+    void mark(const char *label) {
+        if (!on()) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "tmkcl host: %-18s %-22s %8.1f us\n", what, label, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 /* ------------------------------------------------------------------ small device buffer helper */
+/* Device buffers and pinned slots are recycled through a process-wide pool: a task-motion planner builds a
+ * new collision context for every motion query (start-state allowance, reparented objects), and
+ * cudaMalloc / cudaMallocHost / cudaFree cost 1-3 ms per context - more than the query's validity checks. */
+struct DevPool {
+    struct Ent { void *p; size_t cap; int dev; };
+    std::mutex mu;
+    std::vector<Ent> free_;
+    size_t held = 0;
+    static constexpr size_t HELD_MAX = size_t(4) << 30;
+    void *take(size_t bytes, size_t *cap) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = free_.size();
+            for (size_t k = 0; k < free_.size(); k++)
+                if (free_[k].dev == dev && free_[k].cap >= bytes && free_[k].cap <= 4 * bytes + 4096 &&
+                    (best == free_.size() || free_[k].cap < free_[best].cap))
+                    best = k;
+            if (best != free_.size()) {
+                Ent e = free_[best];
+                free_[best] = free_.back();
+                free_.pop_back();
+                held -= e.cap;
+                *cap = e.cap;
+                return e.p;
+            }
+        }
+        void *p = nullptr;
+        *cap = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&p, *cap));
+        return p;
+    }
+    /* the caller guarantees that no work in flight still touches p */
+    void give(void *p, size_t cap) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> g(mu);
+        if (held + cap > HELD_MAX) { cudaFree(p); return; }
+        free_.push_back({p, cap, dev});
+        held += cap;
+    }
+};
+static DevPool g_dev_pool;
+
+struct PinnedPool { /* 64-byte pinned slots (the counters a batch call reads back) */
+    std::mutex mu;
+    std::vector<void *> free_;
+    void *take() {
+        std::lock_guard<std::mutex> g(mu);
+        if (free_.empty()) {
+            char *blk = nullptr;
+            CK(cudaMallocHost((void **)&blk, 4096));
+            for (int k = 0; k < 64; k++) free_.push_back(blk + 64 * k);
+        }
+        void *p = free_.back();
+        free_.pop_back();
+        return p;
+    }
+    void give(void *p) { std::lock_guard<std::mutex> g(mu); free_.push_back(p); }
+};
+static PinnedPool g_pinned_pool;
+
+struct StreamSet { cudaStream_t stream, copy_stream; cudaEvent_t ev[8]; int dev; };
+struct StreamPool { /* the two streams and the copy events of a collision context (idle when returned) */
+    std::mutex mu;
+    std::vector<StreamSet> free_;
+    StreamSet take() {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t k = 0; k < free_.size(); k++)
+                if (free_[k].dev == dev) {
+                    StreamSet ss = free_[k];
+                    free_[k] = free_.back();
+                    free_.pop_back();
+                    return ss;
+                }
+        }
+        StreamSet ss;
+        ss.dev = dev;
+        CK(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ss.copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&ss.ev[k], cudaEventDisableTiming));
+        return ss;
+    }
+    void give(const StreamSet &ss) { std::lock_guard<std::mutex> g(mu); free_.push_back(ss); }
+};
+static StreamPool g_stream_pool;
+
 struct DBuf {
     void *p = nullptr;
     size_t cap = 0;
     void need(size_t bytes) {
         if (bytes <= cap) return;
-        if (p) CK(cudaFree(p));
-        cap = bytes + bytes / 4 + 256;
-        CK(cudaMalloc(&p, cap));
+        if (p) { /* growth: earlier launches may still read the old buffer */
+            CK(cudaDeviceSynchronize());
+            g_dev_pool.give(p, cap);
+        }
+        p = g_dev_pool.take(bytes, &cap);
     }
+    /* only after the streams that used the buffer were synchronised */
     void release() {
-        if (p) cudaFree(p);
+        if (p) g_dev_pool.give(p, cap);
         p = nullptr;
         cap = 0;
     }
@@ -61,6 +171,7 @@ struct SgDev {
 extern "C" void tmk_dev_sg_release(void *dev) {
     SgDev *d = (SgDev *)dev;
     if (!d) return;
+    cudaDeviceSynchronize();
     d->frames.release(); d->q.release(); d->rel.release(); d->ab.release();
     d->b_frames.release(); d->b_q.release(); d->b_out.release();
     delete d;
@@ -172,6 +283,9 @@ static void mesh_compile(const struct aa_rx_mesh *m, HostMesh &hm) {
     hm.brad = sqrt(r2) * (1 + 1e-12);
 }
 
+static std::mutex g_mesh_mu;
+extern "C" void tmk_mesh_compiled_release(void *compiled) { delete (HostMesh *)compiled; }
+
 /* ------------------------------------------------------------------ the collision context */
 struct ImageDev {
     DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, g_cells, g_items, g_live;
@@ -198,7 +312,7 @@ struct aa_rx_cl {
 
     /* frame-relative geometry + meshes */
     std::vector<DGeom<double>> geoms;
-    std::vector<HostMesh> hmesh;
+    std::vector<BvhNode> mesh_root; /* root box of every mesh (the broadphase sees a static mesh as this box) */
     DBuf d_geoms, d_nodes, d_trisf, d_trisd, d_meshf, d_meshd;
 
     /* generic pair list for aa_rx_cl_check */
@@ -245,8 +359,24 @@ static cudaEvent_t *timing_begin(struct aa_rx_cl *cl, cudaStream_t s) {
 
 static void build_geoms(struct aa_rx_cl *cl) {
     const struct aa_rx_sg *sg = cl->sg;
-    cl->hmesh.resize(sg->n_mesh);
-    for (size_t m = 0; m < sg->n_mesh; m++) mesh_compile(sg->meshes[m], cl->hmesh[m]);
+    HostSpan hs("build_geoms");
+    /* the BVH of a mesh is built once and kept with the mesh handle: scene-graph copies share it */
+    std::vector<const HostMesh *> hmesh(sg->n_mesh);
+    cl->mesh_root.resize(sg->n_mesh);
+    {
+        std::lock_guard<std::mutex> g(g_mesh_mu);
+        for (size_t m = 0; m < sg->n_mesh; m++) {
+            struct aa_rx_mesh *mesh = sg->meshes[m];
+            if (!mesh->compiled) {
+                HostMesh *hm = new HostMesh();
+                mesh_compile(mesh, *hm);
+                mesh->compiled = hm;
+            }
+            hmesh[m] = (const HostMesh *)mesh->compiled;
+            cl->mesh_root[m] = hmesh[m]->nodes[0];
+        }
+    }
+    hs.mark("mesh_compile");
     cl->geoms.resize(sg->n_g);
     for (size_t g = 0; g < sg->n_g; g++) {
         DGeom<double> &G = cl->geoms[g];
@@ -269,8 +399,8 @@ static void build_geoms(struct aa_rx_cl *cl) {
             G.brad = sqrt(G.dim[0] * G.dim[0] + G.dim[1] * G.dim[1]);
             break;
         default:
-            for (int a = 0; a < 3; a++) G.dim[a] = cl->hmesh[G.mesh].centre[a];
-            G.brad = cl->hmesh[G.mesh].brad;
+            for (int a = 0; a < 3; a++) G.dim[a] = hmesh[G.mesh]->centre[a];
+            G.brad = hmesh[G.mesh]->brad;
         }
         G.brad *= (1 + 1e-12);
     }
@@ -279,30 +409,31 @@ static void build_geoms(struct aa_rx_cl *cl) {
     std::vector<double> trisd;
     std::vector<float> trisf;
     std::vector<size_t> noff, toff;
-    for (auto &hm : cl->hmesh) {
+    for (const HostMesh *hm : hmesh) {
         noff.push_back(nodes.size());
         toff.push_back(trisd.size());
-        nodes.insert(nodes.end(), hm.nodes.begin(), hm.nodes.end());
-        trisd.insert(trisd.end(), hm.tris.begin(), hm.tris.end());
+        nodes.insert(nodes.end(), hm->nodes.begin(), hm->nodes.end());
+        trisd.insert(trisd.end(), hm->tris.begin(), hm->tris.end());
     }
     trisf.assign(trisd.begin(), trisd.end());
     upload(cl->d_nodes, nodes, cl->stream);
     upload(cl->d_trisf, trisf, cl->stream);
     upload(cl->d_trisd, trisd, cl->stream);
-    std::vector<MeshRef<float>> mf(cl->hmesh.size());
-    std::vector<MeshRef<double>> md(cl->hmesh.size());
-    for (size_t m = 0; m < cl->hmesh.size(); m++) {
+    std::vector<MeshRef<float>> mf(hmesh.size());
+    std::vector<MeshRef<double>> md(hmesh.size());
+    for (size_t m = 0; m < hmesh.size(); m++) {
         mf[m].nodes = md[m].nodes = (const BvhNode *)cl->d_nodes.p + noff[m];
         mf[m].tris = (const float *)cl->d_trisf.p + toff[m];
         md[m].tris = (const double *)cl->d_trisd.p + toff[m];
-        md[m].brad = cl->hmesh[m].brad; mf[m].brad = (float)cl->hmesh[m].brad;
-        md[m].cx = cl->hmesh[m].centre[0]; md[m].cy = cl->hmesh[m].centre[1]; md[m].cz = cl->hmesh[m].centre[2];
+        md[m].brad = hmesh[m]->brad; mf[m].brad = (float)hmesh[m]->brad;
+        md[m].cx = hmesh[m]->centre[0]; md[m].cy = hmesh[m]->centre[1]; md[m].cz = hmesh[m]->centre[2];
         mf[m].cx = (float)md[m].cx; mf[m].cy = (float)md[m].cy; mf[m].cz = (float)md[m].cz;
     }
     upload(cl->d_meshf, mf, cl->stream);
     upload(cl->d_meshd, md, cl->stream);
     upload(cl->d_geoms, cl->geoms, cl->stream);
     CK(cudaStreamSynchronize(cl->stream));
+    hs.mark("uploads");
 }
 
 extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
@@ -311,6 +442,7 @@ extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev < 1) tmk_die("aa_rx_cl_create: no CUDA device (no CPU fallback exists)");
+    HostSpan hs("cl_create");
     struct aa_rx_cl *cl = new aa_rx_cl();
     cl->sg = sg;
     cl->n_f = sg->n_f; cl->n_q = sg->n_q; cl->n_g = sg->n_g; cl->wpr = sg->wpr;
@@ -322,17 +454,23 @@ extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
     cl->timing = 0; cl->ev_used = 0;
     cl->use_tile = getenv("TMK_NO_TILE") ? 0 : 1;
     memset(&cl->stats, 0, sizeof(cl->stats));
-    CK(cudaStreamCreateWithFlags(&cl->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&cl->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&cl->ev_copy[k], cudaEventDisableTiming));
-    CK(cudaMallocHost((void **)&cl->h_cnt, 64));
+    {
+        StreamSet ss = g_stream_pool.take();
+        cl->stream = ss.stream; cl->copy_stream = ss.copy_stream;
+        memcpy(cl->ev_copy, ss.ev, sizeof(ss.ev));
+    }
+    hs.mark("streams+events");
+    cl->h_cnt = (uint32_t *)g_pinned_pool.take();
+    hs.mark("pinned");
     build_geoms(cl);
+    hs.mark("build_geoms");
     return cl;
 }
 
 extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     if (!cl) return;
-    cudaStreamSynchronize(cl->stream);
+    HostSpan hs("cl_destroy");
+    cudaDeviceSynchronize(); /* the scratch buffers go back to the pool: nothing may still use them */
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
                     &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_conv, &cl->d_tri, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
@@ -341,12 +479,17 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     for (auto &g : cl->edge_graphs) cudaGraphExecDestroy(g.exec);
-    cudaFreeHost(cl->h_cnt);
-    for (int k = 0; k < 8; k++) cudaEventDestroy(cl->ev_copy[k]);
-    cudaStreamDestroy(cl->copy_stream);
-    cudaStreamDestroy(cl->stream);
+    g_pinned_pool.give(cl->h_cnt);
+    {
+        StreamSet ss;
+        ss.stream = cl->stream; ss.copy_stream = cl->copy_stream;
+        memcpy(ss.ev, cl->ev_copy, sizeof(ss.ev));
+        CK(cudaGetDevice(&ss.dev));
+        g_stream_pool.give(ss);
+    }
     free(cl->allowed);
     delete cl;
+    hs.mark("all");
 }
 
 extern "C" void aa_rx_cl_allow(struct aa_rx_cl *cl, aa_rx_frame_id i, aa_rx_frame_id j, int allowed) {
@@ -443,6 +586,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
                 0 == memcmp(im.sub.data(), sub_ids, sizeof(int) * n_sub) &&
                 0 == memcmp(im.q_base.data(), q_base, sizeof(double) * n_q);
     if (same) return;
+    HostSpan hs("ensure_image");
     for (size_t k = 0; k < n_sub; k++)
         if (sub_ids[k] < 0 || (size_t)sub_ids[k] >= n_q) tmk_die("batch: bad configuration id %d", sub_ids[k]);
     im.sub.assign(sub_ids, sub_ids + n_sub);
@@ -452,6 +596,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     size_t n_f = cl->n_f;
     std::vector<double> rel(7 * n_f), ab(7 * n_f);
     tmk_dev_fk64(sg, q_base, rel.data(), ab.data()); /* static poses come from the GPU FK */
+    hs.mark("fk64");
 
     std::vector<int> slot(n_f, -1), is_joint(n_f, 0);
     std::vector<double> fold(7 * n_f, 0.0);
@@ -686,13 +831,14 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         Q.brad = (float)(G.brad * (1 + 1e-6));
         Q.h0 = (float)G.dim[0]; Q.h1 = (float)G.dim[1]; Q.h2 = (float)G.dim[2];
         if (G.shape == TMK_MESH) { /* broadphase sees a static mesh as the oriented box of its root node */
-            const BvhNode &root = cl->hmesh[G.mesh].nodes[0];
+            const BvhNode &root = cl->mesh_root[G.mesh];
             Q.h0 = 0.5f * (root.hi[0] - root.lo[0]) * (1 + 1e-6f) + 1e-6f;
             Q.h1 = 0.5f * (root.hi[1] - root.lo[1]) * (1 + 1e-6f) + 1e-6f;
             Q.h2 = 0.5f * (root.hi[2] - root.lo[2]) * (1 + 1e-6f) + 1e-6f;
         }
     }
 
+    hs.mark("host lists");
     /* hoisted static-static pairs, evaluated once (double) */
     std::vector<uint2> sp;
     for (size_t a = 0; a < cl->n_g; a++)
@@ -708,6 +854,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         for (uint8_t o : out) static_hit |= o;
         tmp.release();
     }
+    hs.mark("static pairs");
 
     std::vector<DJoint<float>> jf(joints.size());
     for (size_t k = 0; k < joints.size(); k++) cvt_joint(joints[k], jf[k]);
@@ -737,6 +884,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         upload(im.ps4, ps4, cl->stream);
     }
     CK(cudaStreamSynchronize(cl->stream));
+    hs.mark("uploads");
 
     im.d.joints = (const DJoint<double> *)im.jd.p; im.f.joints = (const DJoint<float> *)im.jf.p;
     im.d.mg = (const DGeom<double> *)im.mgd.p; im.f.mg = (const DGeom<float> *)im.mgf.p;
@@ -773,6 +921,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     if (mg.size() > 64) im.wcfg.smem = im.wcfg_e.smem = -1; /* queue items hold a 6-bit moving-geometry index */
     im.valid = true;
     im.serial++;
+    hs.mark("tile_configure");
 }
 
 /* ------------------------------------------------------------------ batch launches */

@@ -105,12 +105,15 @@ struct aa_rx_mesh *aa_rx_mesh_create(void) {
 void aa_rx_mesh_destroy(struct aa_rx_mesh *m) {
     if (!m) return;
     if (--m->refcount > 0) return;
+    tmk_mesh_compiled_release(m->compiled);
     free(m->verts);
     free(m->idx);
     free(m);
 }
 void aa_rx_mesh_set_vertices(struct aa_rx_mesh *m, size_t n, const float *v, int copy) {
     (void)copy; /* always copied: the handle owns its data */
+    tmk_mesh_compiled_release(m->compiled);
+    m->compiled = NULL;
     free(m->verts);
     m->nv = n;
     m->verts = (float *)malloc(sizeof(float) * 3 * n);
@@ -118,6 +121,8 @@ void aa_rx_mesh_set_vertices(struct aa_rx_mesh *m, size_t n, const float *v, int
 }
 void aa_rx_mesh_set_indices(struct aa_rx_mesh *m, size_t n, const unsigned *idx, int copy) {
     (void)copy;
+    tmk_mesh_compiled_release(m->compiled);
+    m->compiled = NULL;
     free(m->idx);
     m->nt = n;
     m->idx = (unsigned *)malloc(sizeof(unsigned) * 3 * n);

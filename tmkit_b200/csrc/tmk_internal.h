@@ -21,7 +21,9 @@ struct aa_rx_mesh {
     float *verts; /* nv*3 */
     size_t nt;   /* triangles */
     unsigned *idx; /* nt*3 */
+    void *compiled; /* BVH built by the first collision context that sees the mesh (owned by cl.cu) */
 };
+void tmk_mesh_compiled_release(void *compiled);
 
 struct aa_rx_geom {
     int shape;
