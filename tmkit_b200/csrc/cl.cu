@@ -19,6 +19,7 @@
 
 #include "kernels.cuh"
 #include "pipeline.cuh"
+#include "ik.cuh"
 #include "tmk_internal.h"
 
 using namespace tmk;
@@ -164,7 +165,8 @@ template <typename T> static void upload(DBuf &b, const std::vector<T> &v, cudaS
 /* ------------------------------------------------------------------ scene-graph device mirror (FK) */
 struct SgDev {
     DBuf frames, q, rel, ab;
-    DBuf b_frames, b_q, b_out; /* aa_rx_sg_tf_batch scratch (kept: IK calls it once per iteration) */
+    DBuf b_frames, b_q, b_out; /* aa_rx_sg_tf_batch scratch */
+    DBuf ik_in, ik_out;        /* tmk_dev_ik: one upload, one launch, one download per goal */
     size_t n_f = 0;
 };
 
@@ -174,6 +176,7 @@ extern "C" void tmk_dev_sg_release(void *dev) {
     cudaDeviceSynchronize();
     d->frames.release(); d->q.release(); d->rel.release(); d->ab.release();
     d->b_frames.release(); d->b_q.release(); d->b_out.release();
+    d->ik_in.release(); d->ik_out.release();
     delete d;
 }
 
@@ -209,6 +212,70 @@ extern "C" void tmk_dev_fk64(const struct aa_rx_sg *sg, const double *q, double 
     CK(cudaGetLastError());
     CK(cudaMemcpy(TF_rel, d->rel.p, sizeof(double) * 7 * sg->n_f, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(TF_abs, d->ab.p, sizeof(double) * 7 * sg->n_f, cudaMemcpyDeviceToHost));
+}
+
+/* Damped-least-squares IK of a kinematic chain for n_seed start guesses, all iterations in one launch
+ * (ik.cuh).  frames[0..n_fr) is the parent-linked path from the chain root to the tip.  Q (n_seed x n_sub)
+ * holds the seeds on entry and the final iterates on return, err (n_seed x 2) their position / rotation
+ * error; a seed converged iff both are below tol.  Returns the number of iterations run. */
+extern "C" int tmk_dev_ik(const struct aa_rx_sg *sg, size_t n_fr, const aa_rx_frame_id *frames, size_t n_sub,
+                          const aa_rx_config_id *sub_ids, const double *q_all_base, const double *lo, const double *hi,
+                          const double *goal, size_t n_seed, double *Q, double *err, int max_iter, int enough,
+                          int min_iter, double tol) {
+    if (n_seed < 1 || n_seed > 32) tmk_die("tmk_dev_ik: n_seed = %zu outside 1..32", n_seed);
+    if (n_sub < 1 || n_sub > TMK_IK_MAXCOL) tmk_die("tmk_dev_ik: n_sub = %zu outside 1..%d", n_sub, TMK_IK_MAXCOL);
+    if (n_fr < 1) tmk_die("tmk_dev_ik: empty chain");
+    SgDev *d = sg_dev(sg);
+    IkParams P;
+    memset(&P, 0, sizeof(P));
+    P.base[3] = 1.0;
+    const int root = sg->parent[frames[0]];
+    if (root >= 0) { /* chain hanging off an inner frame: its pose at the base configuration */
+        std::vector<double> rel(7 * sg->n_f), ab(7 * sg->n_f);
+        tmk_dev_fk64(sg, q_all_base, rel.data(), ab.data());
+        memcpy(P.base, &ab[7 * (size_t)root], sizeof(double) * 7);
+    }
+    memcpy(P.goal, goal, sizeof(double) * 7);
+    P.n_fr = (int)n_fr; P.n_sub = (int)n_sub; P.n_seed = (int)n_seed; P.max_iter = max_iter;
+    P.enough = enough; P.min_iter = min_iter; P.tol = tol;
+    /* one staging block: frames | lo | hi | Q */
+    const size_t b_fr = sizeof(IkFrame) * n_fr, b_lim = sizeof(double) * n_sub, b_q = sizeof(double) * n_seed * n_sub;
+    std::vector<unsigned char> in(b_fr + 2 * b_lim + b_q);
+    IkFrame *fr = (IkFrame *)in.data();
+    for (size_t f = 0; f < n_fr; f++) {
+        const int i = frames[f];
+        if (i < 0 || (size_t)i >= sg->n_f) tmk_die("tmk_dev_ik: bad frame id %d", i);
+        if (f > 0 && sg->parent[i] != frames[f - 1]) tmk_die("tmk_dev_ik: frames are not a parent-linked chain");
+        memcpy(fr[f].E, sg->E + 7 * (size_t)i, sizeof(double) * 7);
+        memcpy(fr[f].ax, sg->axis + 3 * (size_t)i, sizeof(double) * 3);
+        fr[f].off = sg->offset[i];
+        fr[f].type = sg->type[i];
+        fr[f].col = -1;
+        fr[f].qfix = 0.0;
+        if (fr[f].type != TMK_FIXED) {
+            fr[f].qfix = q_all_base[sg->qidx[i]];
+            for (size_t k = 0; k < n_sub; k++)
+                if (sub_ids[k] == sg->qidx[i]) fr[f].col = (int)k;
+        }
+    }
+    memcpy(in.data() + b_fr, lo, b_lim);
+    memcpy(in.data() + b_fr + b_lim, hi, b_lim);
+    memcpy(in.data() + b_fr + 2 * b_lim, Q, b_q);
+    d->ik_in.need(in.size());
+    const size_t b_err = sizeof(double) * 2 * n_seed;
+    d->ik_out.need(b_err + 16);
+    CK(cudaMemcpy(d->ik_in.p, in.data(), in.size(), cudaMemcpyHostToDevice));
+    unsigned char *di = (unsigned char *)d->ik_in.p, *dout = (unsigned char *)d->ik_out.p;
+    k_ik_dls<<<1, 32>>>((const IkFrame *)di, P, (const double *)(di + b_fr), (const double *)(di + b_fr + b_lim),
+                        (double *)(di + b_fr + 2 * b_lim), (double *)dout, (int *)(dout + b_err));
+    CK(cudaGetLastError());
+    std::vector<unsigned char> out(b_err + 16);
+    CK(cudaMemcpy(out.data(), dout, out.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(Q, di + b_fr + 2 * b_lim, b_q, cudaMemcpyDeviceToHost));
+    memcpy(err, out.data(), b_err);
+    int iters = 0;
+    memcpy(&iters, out.data() + b_err, sizeof(int));
+    return iters;
 }
 
 /* ------------------------------------------------------------------ mesh BVH (host build) */

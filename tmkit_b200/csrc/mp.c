@@ -184,105 +184,7 @@ int aa_rx_mp_set_goal(struct aa_rx_mp *mp, size_t n_sub, const double *q_sub) {
 }
 
 /* ------------------------------------------------------------------ inverse kinematics */
-/* solve (A + lambda^2 I) x = b for symmetric positive definite 6x6 A (Cholesky) */
-static int solve6(double A[6][6], const double *b, double lambda2, double *x) {
-    double L[6][6];
-    memset(L, 0, sizeof(L));
-    for (int i = 0; i < 6; i++) {
-        for (int j = 0; j <= i; j++) {
-            double s = A[i][j] + (i == j ? lambda2 : 0.0);
-            for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-            if (i == j) {
-                if (s <= 0) return -1;
-                L[i][i] = sqrt(s);
-            } else L[i][j] = s / L[j][j];
-        }
-    }
-    double y[6];
-    for (int i = 0; i < 6; i++) {
-        double s = b[i];
-        for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
-        y[i] = s / L[i][i];
-    }
-    for (int i = 5; i >= 0; i--) {
-        double s = y[i];
-        for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
-        x[i] = s / L[i][i];
-    }
-    return 0;
-}
-
-/* pose error of tip vs goal (6-vector: translation, rotation vector) */
-static void pose_error(const double *tip, const double *goal, double *e) {
-    for (int k = 0; k < 3; k++) e[k] = goal[4 + k] - tip[4 + k];
-    double c[4] = {-tip[0], -tip[1], -tip[2], tip[3]}, d[4];
-    tmk_qmul(goal, c, d); /* goal * conj(tip) */
-    double sgn = d[3] < 0 ? -1.0 : 1.0;
-    double vn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    double ang = 2.0 * atan2(vn, sgn * d[3]);
-    double sc = vn > 1e-12 ? sgn * ang / vn : 2.0 * sgn;
-    for (int k = 0; k < 3; k++) e[3 + k] = sc * d[k];
-}
-
-/* one damped-least-squares step for one candidate from the absolute poses of the chain frames */
-static void ik_step(const struct aa_rx_mp *mp, size_t n_fr, const aa_rx_frame_id *frames, const double *tf /* n_fr x 7 */,
-                    const double *goal, double *q, double *err_p, double *err_o) {
-    const double *tip = tf + 7 * (n_fr - 1);
-    double e[6];
-    pose_error(tip, goal, e);
-    *err_p = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-    *err_o = sqrt(e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
-    double J[6][TMK_MP_MAXSUB];
-    memset(J, 0, sizeof(J));
-    for (size_t f = 0; f < n_fr; f++) {
-        int type = aa_rx_sg_frame_type(mp->sg, frames[f]);
-        if (type == TMK_FIXED) continue;
-        int cid = aa_rx_sg_frame_config(mp->sg, frames[f]);
-        size_t col = 0;
-        while (col < mp->n_sub && mp->ids[col] != cid) col++;
-        if (col == mp->n_sub) continue;
-        double ax[3], aw[3];
-        aa_rx_sg_frame_axis(mp->sg, frames[f], ax);
-        double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
-        for (int k = 0; k < 3; k++) ax[k] /= an;
-        const double *F = tf + 7 * f;
-        tmk_qrot(F, ax, aw);
-        if (type == TMK_REVOLUTE) {
-            double r[3] = {tip[4] - F[4], tip[5] - F[5], tip[6] - F[6]};
-            J[0][col] += aw[1] * r[2] - aw[2] * r[1];
-            J[1][col] += aw[2] * r[0] - aw[0] * r[2];
-            J[2][col] += aw[0] * r[1] - aw[1] * r[0];
-            for (int k = 0; k < 3; k++) J[3 + k][col] += aw[k];
-        } else {
-            for (int k = 0; k < 3; k++) J[k][col] += aw[k];
-        }
-    }
-    double A[6][6];
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) {
-            double s = 0;
-            for (size_t k = 0; k < mp->n_sub; k++) s += J[i][k] * J[j][k];
-            A[i][j] = s;
-        }
-    double en = *err_p + *err_o;
-    double lambda2 = fmin(1e-2, 1e-2 * en * en) + 1e-9; /* damping shrinks as the solution is approached */
-    double y[6];
-    if (solve6(A, e, lambda2, y) != 0) return;
-    double big = 0, dq[TMK_MP_MAXSUB];
-    for (size_t k = 0; k < mp->n_sub; k++) {
-        double s = 0;
-        for (int i = 0; i < 6; i++) s += J[i][k] * y[i];
-        dq[k] = s;
-        if (fabs(s) > big) big = fabs(s);
-    }
-    double scale = big > 0.4 ? 0.4 / big : 1.0;
-    for (size_t k = 0; k < mp->n_sub; k++) {
-        q[k] += scale * dq[k];
-        if (q[k] < mp->lo[k]) q[k] = mp->lo[k];
-        if (q[k] > mp->hi[k]) q[k] = mp->hi[k];
-    }
-}
-
+/* damped least squares over the chain, evaluated on the device for all seeds at once: ik.cuh */
 int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
     if (!mp->have_start) tmk_die("aa_rx_mp_set_wsgoal: set the start first");
     double t0 = now_s();
@@ -294,8 +196,6 @@ int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
     size_t n_fr = tmk_sub_frames(mp->ssg, &frames);
     const size_t S = MP_IK_SEEDS, n = mp->n_sub;
     double *Q = (double *)malloc(sizeof(double) * S * n);
-    double *TF = (double *)malloc(sizeof(double) * S * n_fr * 7);
-    uint8_t *done = (uint8_t *)calloc(S, 1);
     for (size_t s = 0; s < S; s++)
         for (size_t k = 0; k < n; k++) {
             double q0 = mp->q_start_all[mp->ids[k]];
@@ -306,70 +206,34 @@ int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
                 Q[s * n + k] = fmin(mp->hi[k], fmax(mp->lo[k], v));
             } else Q[s * n + k] = mp->lo[k] + rng_unit(&mp->rng) * (mp->hi[k] - mp->lo[k]);
         }
-    /* lock-step iterations: one batched FK (GPU) per iteration for all candidates */
-    size_t n_done = 0;
-    /* stop early once plenty of candidates have converged and the stragglers had their chance */
-    for (int it = 0; it < MP_IK_ITERS && n_done < S && !(n_done >= 8 && it >= 16); it++) {
-        aa_rx_sg_tf_batch(mp->sg, S, n, mp->ids, mp->n_all, mp->q_start_all, Q, n, n_fr, frames, TF);
-        mp->st.n_ik_iterations++;
-        for (size_t s = 0; s < S; s++) {
-            if (done[s]) continue;
-            double ep, eo;
-            double before[TMK_MP_MAXSUB];
-            memcpy(before, Q + s * n, sizeof(double) * n);
-            ik_step(mp, n_fr, frames, TF + s * n_fr * 7, goal, Q + s * n, &ep, &eo);
-            if (ep < 2e-5 && eo < 2e-5) { /* FP32 FK accuracy; polished in double below */
-                memcpy(Q + s * n, before, sizeof(double) * n);
-                done[s] = 1;
-                n_done++;
-            }
-        }
-    }
-    /* polish the converged candidates with the double-precision single-configuration FK */
-    size_t n_f = aa_rx_sg_frame_count(mp->sg);
-    double *ab = (double *)malloc(sizeof(double) * 7 * (n_f + 1));
-    double *chain = (double *)malloc(sizeof(double) * 7 * (n_fr + 1));
-    double *q_all = (double *)malloc(sizeof(double) * (mp->n_all + 1));
+    /* all seeds iterated to convergence in one launch (double precision, ik.cuh) */
+    double *err = (double *)malloc(sizeof(double) * 2 * S);
+    const double tol = 1e-9;
+    mp->st.n_ik_iterations += (size_t)tmk_dev_ik(mp->sg, n_fr, frames, n, mp->ids, mp->q_start_all, mp->lo, mp->hi, goal, S, Q,
+                                                 err, MP_IK_ITERS, 8, 16, tol);
     double cand[MP_IK_SEEDS][TMK_MP_MAXSUB];
     double cand_cost[MP_IK_SEEDS];
     size_t n_cand = 0;
-    /* nearest to the start first; the double-precision polish is a GPU round trip per iteration, so only
-     * the MP_IK_POLISH most promising candidates get it */
+    /* nearest to the start first; the MP_IK_POLISH most promising converged candidates are kept */
     size_t order[MP_IK_SEEDS], n_ord = 0;
     double ocost[MP_IK_SEEDS];
-    {
-        double start_sub[TMK_MP_MAXSUB];
-        for (size_t k = 0; k < n; k++) start_sub[k] = mp->q_start_all[mp->ids[k]];
-        for (size_t s = 0; s < S; s++) {
-            if (!done[s]) continue;
-            double c = dist(Q + s * n, start_sub, n);
-            size_t pos = n_ord++;
-            while (pos > 0 && ocost[pos - 1] > c) { order[pos] = order[pos - 1]; ocost[pos] = ocost[pos - 1]; pos--; }
-            order[pos] = s; ocost[pos] = c;
-        }
+    double start_sub[TMK_MP_MAXSUB];
+    for (size_t k = 0; k < n; k++) start_sub[k] = mp->q_start_all[mp->ids[k]];
+    for (size_t s = 0; s < S; s++) {
+        if (!(err[2 * s] < tol && err[2 * s + 1] < tol)) continue;
+        double c = dist(Q + s * n, start_sub, n);
+        size_t pos = n_ord++;
+        while (pos > 0 && ocost[pos - 1] > c) { order[pos] = order[pos - 1]; ocost[pos] = ocost[pos - 1]; pos--; }
+        order[pos] = s; ocost[pos] = c;
     }
-    for (size_t oi = 0; oi < n_ord && oi < MP_IK_POLISH; oi++) {
-        const size_t s = order[oi];
-        double *q = Q + s * n;
-        double ep = 1, eo = 1;
-        for (int it = 0; it < 6; it++) {
-            memcpy(q_all, mp->q_start_all, sizeof(double) * mp->n_all);
-            aa_rx_sg_config_set(mp->sg, mp->n_all, n, mp->ids, q, q_all);
-            aa_rx_sg_tf(mp->sg, mp->n_all, q_all, n_f, NULL, 7, ab, 7);
-            for (size_t f = 0; f < n_fr; f++) memcpy(chain + 7 * f, ab + 7 * (size_t)frames[f], sizeof(double) * 7);
-            double before[TMK_MP_MAXSUB];
-            memcpy(before, q, sizeof(double) * n);
-            ik_step(mp, n_fr, frames, chain, goal, q, &ep, &eo);
-            if (ep < 1e-9 && eo < 1e-9) { memcpy(q, before, sizeof(double) * n); break; }
-        }
-        if (ep > 1e-7 || eo > 1e-7 || !in_limits(mp, q)) continue;
+    for (size_t oi = 0; oi < n_ord && n_cand < MP_IK_POLISH; oi++) {
+        const double *q = Q + order[oi] * n;
+        if (!in_limits(mp, q)) continue;
         int dup = 0;
         for (size_t c = 0; c < n_cand; c++) dup |= dist(cand[c], q, n) < 1e-3;
         if (dup) continue;
         memcpy(cand[n_cand], q, sizeof(double) * n);
-        double start_sub[TMK_MP_MAXSUB];
-        for (size_t k = 0; k < n; k++) start_sub[k] = mp->q_start_all[mp->ids[k]];
-        cand_cost[n_cand] = dist(q, start_sub, n);
+        cand_cost[n_cand] = ocost[oi];
         n_cand++;
     }
     /* collision-free candidates, nearest to the start first */
@@ -386,7 +250,7 @@ int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
             bits[best >> 5] &= ~(1u << (best & 31));
         }
     }
-    free(Q); free(TF); free(done); free(ab); free(chain); free(q_all);
+    free(Q); free(err);
     mp->st.n_goals = mp->n_goal;
     mp->st.ik_s += now_s() - t0;
     return (int)mp->n_goal;

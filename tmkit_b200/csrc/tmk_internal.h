@@ -112,6 +112,11 @@ size_t tmk_sub_frames(const struct aa_rx_sg_sub *s, const aa_rx_frame_id **frame
 /* implemented in cl.cu */
 void tmk_dev_sg_release(void *dev);
 void tmk_dev_fk64(const struct aa_rx_sg *sg, const double *q, double *TF_rel, double *TF_abs); /* dense n_f x 7 */
+/* cl.cu: all-iterations-on-the-device IK of a parent-linked chain (see ik.cuh) */
+int tmk_dev_ik(const struct aa_rx_sg *sg, size_t n_fr, const aa_rx_frame_id *frames, size_t n_sub,
+               const aa_rx_config_id *sub_ids, const double *q_all_base, const double *lo, const double *hi,
+               const double *goal, size_t n_seed, double *Q, double *err, int max_iter, int enough, int min_iter,
+               double tol);
 
 #ifdef __cplusplus
 }
