@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <chrono>
 #include <mutex>
@@ -401,6 +402,7 @@ struct aa_rx_cl {
      * a CUDA graph and replayed, otherwise the host cannot enqueue as fast as the GPU executes */
     struct EdgeGraph { uint64_t key[12]; cudaGraphExec_t exec; uint64_t used; size_t n_kernels; };
     std::vector<EdgeGraph> edge_graphs;
+    std::vector<std::array<uint64_t, 12>> edge_seen; /* argument keys seen once (no graph yet) */
     uint64_t graph_clock = 0;
     UncList cur_unc;      /* undecided list of the batch in flight */
     cudaEvent_t *cur_ev;  /* its timing events (NULL when timing is off) */
@@ -1128,7 +1130,8 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
 }
 
 static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, const void *dQ1, int layout, size_t ld,
-                         double seg_len, uint32_t *d_bits, int32_t *d_first, cudaStream_t s) {
+                         double seg_len, uint32_t *d_bits, int32_t *d_first, cudaStream_t s,
+                         int n_levels = TMK_EDGE_LEVELS) {
     ImageDev &im = cl->img;
     if (!(seg_len > 0)) tmk_die("edges: seg_len must be positive");
     if (n_edge > 0x7ffffff0u) tmk_die("edges: more than 2^31 edges in one call");
@@ -1143,8 +1146,8 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         cl->d_efirst.need(sizeof(int32_t) * n_edge);
         cl->d_alive0.need(sizeof(uint32_t) * n_edge);
         cl->d_alive1.need(sizeof(uint32_t) * n_edge);
-        const bool use_graph = !cl->timing && !getenv("TMK_NO_GRAPH");
-        uint64_t key[12] = {(uint64_t)n_edge, (uint64_t)(uintptr_t)dQ0, (uint64_t)(uintptr_t)dQ1, (uint64_t)layout * 1315423911u + ld,
+        bool use_graph = !cl->timing && !getenv("TMK_NO_GRAPH");
+        uint64_t key[12] = {(uint64_t)n_edge | ((uint64_t)n_levels << 40), (uint64_t)(uintptr_t)dQ0, (uint64_t)(uintptr_t)dQ1, (uint64_t)layout * 1315423911u + ld,
                             0, (uint64_t)(uintptr_t)d_bits, (uint64_t)(uintptr_t)d_first, (uint64_t)(uintptr_t)s, im.serial,
                             (uint64_t)(uintptr_t)cl->d_unc.p ^ ((uint64_t)(uintptr_t)cl->d_mesh.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_conv.p << 2),
                             (uint64_t)(uintptr_t)cl->d_nd.p ^ ((uint64_t)(uintptr_t)cl->d_efirst.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_alive0.p << 2) ^
@@ -1159,7 +1162,17 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
                     cl->stats.n_launches += g.n_kernels; /* kernels run, not API calls */
                     return;
                 }
-            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+            /* a graph is built for arguments seen before: a planner's batches differ call by call and
+             * capture + instantiation costs more than enqueueing the launches once */
+            bool seen = false;
+            for (auto &k : cl->edge_seen) seen |= 0 == memcmp(k.data(), key, sizeof(key));
+            if (!seen) {
+                std::array<uint64_t, 12> k;
+                memcpy(k.data(), key, sizeof(key));
+                if (cl->edge_seen.size() >= 32) cl->edge_seen.erase(cl->edge_seen.begin());
+                cl->edge_seen.push_back(k);
+                use_graph = false;
+            } else CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
         }
         CK(cudaMemsetAsync(cl->d_cnt.p, 0, 512, s));
         /* d_cnt: [0] undecided count, [1] overflow, [2..3] evaluated states, [8 + L] alive count of level L */
@@ -1181,20 +1194,20 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
          * through atomicMin - the price is the few edges that bisect one level further than needed */
         const unsigned hmask = getenv("TMK_EDGE_HEAVY_MASK") ? (unsigned)strtoul(getenv("TMK_EDGE_HEAVY_MASK"), nullptr, 0) : 0x2222u;
         int group0 = 0;
-        for (int L = 0; L < TMK_EDGE_LEVELS; L++) {
+        for (int L = 0; L < n_levels; L++) {
             src.alive = cur_alive; src.n_alive = cur_n; src.level = L;
             u.mesh_n = cnt + 32 + group0; u.conv_n = cnt + 48 + group0; u.tri_n = cnt + 64 + group0;
             launch_tile<SrcEdgeLevel, SinkEdgeFirst>(im.f, im.wcfg_e, src, sink, u, (unsigned long long *)(cnt + 2),
                                                      (unsigned)im.wcfg_e.grid, s);
             CK(cudaGetLastError());
             launches++;
-            if (((hmask >> L) & 1) || L + 1 == TMK_EDGE_LEVELS) {
+            if (((hmask >> L) & 1) || L + 1 == n_levels) {
                 k_heavy_mixed<SrcEdgeLevel, SinkEdgeFirst><<<148 * 4, 128, 0, s>>>(im.f, src, sink, u);
                 CK(cudaGetLastError());
                 launches++;
                 group0 = L + 1;
             }
-            if (L + 1 < TMK_EDGE_LEVELS) {
+            if (L + 1 < n_levels) {
                 uint32_t *out = alive[L & 1], *n_out = cnt + 8 + L;
                 k_edges_compact<<<148 * 2, 256, 0, s>>>(cur_alive, cur_n, ne, nd, first, L, out, n_out);
                 CK(cudaGetLastError());
@@ -1352,8 +1365,28 @@ extern "C" size_t aa_rx_cl_check_edges(struct aa_rx_cl *cl, size_t n_edge, size_
         CK(cudaMemcpyAsync(cl->d_q.p, Q0, n_edge * ldQ * 8, cudaMemcpyHostToDevice, cl->stream));
         CK(cudaMemcpyAsync(cl->d_q1.p, Q1, n_edge * ldQ * 8, cudaMemcpyHostToDevice, cl->stream));
     }
+    /* small batches (a planner's frontier): the longest edge bounds the bisection depth, and the dead levels
+     * are launches the host can see and skip.  +2 segments of slack: the device count is authoritative. */
+    int n_levels = TMK_EDGE_LEVELS;
+    if (n_edge && n_edge <= 4096 && seg_len > 0) {
+        double s2max = 0;
+        for (size_t e = 0; e < n_edge; e++) {
+            double s2 = 0;
+            for (size_t k = 0; k < n_sub; k++) {
+                const double dq = Q1[e * ldQ + k] - Q0[e * ldQ + k];
+                s2 += dq * dq;
+            }
+            if (s2 > s2max) s2max = s2;
+        }
+        const double nd_max = ceil(sqrt(s2max) / seg_len) + 2;
+        if (nd_max < (double)(1 << (TMK_EDGE_LEVELS - 1))) {
+            int L = 1; /* positions 2^(L-1) .. 2^L - 1 live at level L */
+            while ((1 << (L - 1)) < (int)nd_max) L++;
+            n_levels = std::min(TMK_EDGE_LEVELS, L);
+        }
+    }
     launch_edges(cl, n_edge, cl->d_q.p, cl->d_q1.p, TMK_Q_ROWS_F64, ldQ, seg_len, (uint32_t *)cl->d_bits.p,
-                 first_invalid ? (int32_t *)cl->d_first.p : nullptr, cl->stream);
+                 first_invalid ? (int32_t *)cl->d_first.p : nullptr, cl->stream, n_levels);
     if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
     if (first_invalid && n_edge)
         CK(cudaMemcpyAsync(first_invalid, cl->d_first.p, sizeof(int32_t) * n_edge, cudaMemcpyDeviceToHost, cl->stream));
