@@ -269,6 +269,10 @@ def run_sussman(args):
                          "sample": f"oracle replay of the {n_edges} edges one plan checked (validity work only)",
                          "single_thread_s": cpu["1"]},
         "validity_s_gpu": split.get("rrt", 0.0) + split.get("simplify", 0.0),
+        # the whole plan already runs through the host-buffer C calls (aa_rx_mp_*): value IS end to end
+        "e2e": {"value": tot, "unit": "s", "h2d_bytes_per_step": int(2 * 8 * 7 * r.counters["edges_checked"]),
+                "d2h_bytes_per_step": int(4 * ((r.counters["edges_checked"] + 31) // 32 + r.counters["edge_calls"])),
+                "call": "aa_rx_mp_set_start / _set_wsgoal / _plan per action", "note": "bytes: edge end points in, validity words out"},
     }
     print(json.dumps(line))
 
