@@ -23,6 +23,17 @@ import time
 
 import numpy as np
 
+# stdout carries the one JSON line and nothing else: library banners written to fd 1 (NCCL prints its version
+# there) go to stderr instead
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -202,7 +213,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of Amino/FCL semantics (the reference's Amino/FCL/OMPL are not in the tree)",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def metric_name(workload):
@@ -274,7 +285,7 @@ def run_sussman(args):
                 "d2h_bytes_per_step": int(4 * ((r.counters["edges_checked"] + 31) // 32 + r.counters["edge_calls"])),
                 "call": "aa_rx_mp_set_start / _set_wsgoal / _plan per action", "note": "bytes: edge end points in, validity words out"},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -337,23 +348,43 @@ def main():
             ring.append(torch.from_numpy(np.ascontiguousarray(Q.T.astype(np.float32))).to(dev))
             if r < 2:
                 host_rows.append(torch.from_numpy(Q).pin_memory())
-    bits = torch.zeros(nw, dtype=torch.int32, device=dev)
-    gathered = torch.zeros(nw * world, dtype=torch.int32, device=dev) if world > 1 else None
+    # two result buffers: the all-gather of step k (communication stream) overlaps the kernels of step k+1
+    bits2 = [torch.zeros(nw, dtype=torch.int32, device=dev) for _ in range(2)]
+    bits = bits2[0]
+    gathered2 = [torch.zeros(nw * world, dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
     # a dedicated stream: the C ABI takes a cudaStream_t (NULL would mean the handle's own stream),
     # and the events below must be recorded on the stream the kernels are launched on
     ts = torch.cuda.Stream(device=dev)
     stream = ts.cuda_stream
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    cs = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_done = [torch.cuda.Event() for _ in range(2)]      # kernels of the step wrote bits2[b]
+    ev_gathered = [torch.cuda.Event() for _ in range(2)]  # the all-gather has read bits2[b]
+
     def step(i):
         k = i % RING
+        b = i & 1 if world > 1 else 0
+        out = bits2[b]
+        if world > 1:
+            ts.wait_event(ev_gathered[b])  # the gather of step i-2 is done with this buffer
         if edges:
             cl.check_edges_dev(n_units, sub, q0, ring[k].data_ptr(), ring1[k].data_ptr(), A.Q_SOA_F32, n_units, seg,
-                               bits.data_ptr(), 0, stream)
+                               out.data_ptr(), 0, stream)
         else:
-            cl.check_batch_dev(n_units, sub, q0, ring[k].data_ptr(), A.Q_SOA_F32, n_units, bits.data_ptr(), stream)
+            cl.check_batch_dev(n_units, sub, q0, ring[k].data_ptr(), A.Q_SOA_F32, n_units, out.data_ptr(), stream)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, bits)
+            ev_done[b].record(ts)
+            cs.wait_event(ev_done[b])
+            with torch.cuda.stream(cs):
+                dist.all_gather_into_tensor(gathered2[b], out)
+                ev_gathered[b].record(cs)
+
+    def drain():
+        """the timed stream waits for the gathers still in flight: they belong to the timed steps"""
+        if world > 1:
+            ts.wait_event(ev_gathered[0])
+            ts.wait_event(ev_gathered[1])
 
     def barrier():
         if world > 1:
@@ -380,6 +411,7 @@ def main():
             step(args.warmup + i)
             if rank == 0 and i % 16 == 8:
                 sampler.sample_now()  # while the GPU is busy with the steps already queued
+        drain()
         ev[1].record(ts)
         host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps
         barrier()
@@ -397,7 +429,13 @@ def main():
     rk_ms = rk_ms_sum / n_timed
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # per-rank step time, kernel time and host enqueue time (diagnostics beside the max the contract asks for)
+        mine = torch.tensor([ms_total / args.steps, k_ms + rk_ms, host_enqueue_ms], dtype=torch.float64, device=dev)
+        allr = torch.zeros(3 * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = [[round(float(x), 4) for x in allr[3 * r:3 * r + 3].tolist()] for r in range(world)]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
@@ -483,11 +521,14 @@ def main():
         "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args.workload),
+        "config": dict(config_dict(args.workload), parallelism=f"dp{world}: contiguous slice per rank" + (
+            ", one NCCL all-gather of the validity words per step on a second stream (overlaps the next step; "
+            "all gathers finish inside the timed region)" if world > 1 else "")),
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "aa_rx_cl_check_edges" if edges else "aa_rx_cl_check_batch", "host_dtype": "f64 rows, pinned"},
         "gpu_launches": int(launches_per_step * args.steps),
         "host_enqueue_ms_per_step": host_enqueue_ms,
+        "per_rank_ms": per_rank,  # [step, kernels, host enqueue] per rank
         "clocks": clocks,
         # the path is bound by the FP32 (FMA) pipe, not HBM and not the tensor cores (SURVEY.md 8d,
         # DESIGN.md): `roofline` is the FP32 one, `roofline_hbm` the contract's HBM form beside it
@@ -511,7 +552,7 @@ def main():
         v, cores, sample, n, dt = cpu_baseline(args.workload)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
                                 "note": "CPU restatement of Amino/FCL semantics (oracle, early-out mode)"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
