@@ -393,7 +393,10 @@ def main():
 
     with torch.cuda.stream(ts):
         l2_flush.zero_()
-        for i in range(args.warmup):
+        # the swept-edge entry point captures a CUDA graph the second time it sees the same arguments: the
+        # untimed warm-up goes twice around the ring so that the timed steps replay graphs (steady state)
+        n_warm = max(args.warmup, 2 * RING) if edges else args.warmup
+        for i in range(n_warm):
             step(i)
         barrier()
         sampler = ClockSampler(local)
@@ -408,7 +411,7 @@ def main():
         ev[0].record(ts)
         t_host = time.perf_counter()
         for i in range(args.steps):
-            step(args.warmup + i)
+            step(n_warm + i)
             if rank == 0 and i % 16 == 8:
                 sampler.sample_now()  # while the GPU is busy with the steps already queued
         drain()
@@ -419,7 +422,7 @@ def main():
         if not inline_timing:
             cl.kernel_timing(True)
             for i in range(args.steps):
-                step(args.warmup + i)
+                step(n_warm + i)
             barrier()
         n_timed, k_ms_sum, rk_ms_sum = cl.kernel_time()
         cl.kernel_timing(False)

@@ -482,7 +482,10 @@ static void build_geoms(struct aa_rx_cl *cl) {
         noff.push_back(nodes.size());
         toff.push_back(trisd.size());
         nodes.insert(nodes.end(), hm->nodes.begin(), hm->nodes.end());
-        trisd.insert(trisd.end(), hm->tris.begin(), hm->tris.end());
+        for (size_t t = 0; t < hm->tris.size() / 9; t++) { /* 9 -> TMK_TRI_STRIDE values per triangle */
+            trisd.insert(trisd.end(), hm->tris.begin() + 9 * t, hm->tris.begin() + 9 * t + 9);
+            trisd.insert(trisd.end(), TMK_TRI_STRIDE - 9, 0.0);
+        }
     }
     trisf.assign(trisd.begin(), trisd.end());
     upload(cl->d_nodes, nodes, cl->stream);
@@ -1019,10 +1022,13 @@ static void launch_tile(const Image<float> &f, const TileCfg &cfg, const Src &sr
  * list is filled by the traversal) */
 template <class Src, class Sink>
 static void launch_heavy(const Image<float> &f, const Src &src, const Sink &sink, const UncList &u, unsigned ctas,
-                         cudaStream_t s) {
+                         cudaStream_t s, uint32_t *trav_next) {
     k_conv_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
     CK(cudaGetLastError());
-    k_mesh_traverse<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
+    static const bool simple = getenv("TMK_TRAVERSE_SIMPLE") != nullptr; /* A/B aid */
+    static const unsigned trav_ctas = getenv("TMK_TRAV_CTAS") ? (unsigned)atoi(getenv("TMK_TRAV_CTAS")) : 7u;
+    if (simple) k_mesh_traverse_simple<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
+    else k_mesh_traverse<Src, Sink><<<148 * trav_ctas, 128, 0, s>>>(f, src, sink, u, trav_next);
     CK(cudaGetLastError());
     k_tri_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
     CK(cudaGetLastError());
@@ -1048,7 +1054,7 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     if (const char *e = getenv("TMK_MESH_CAP")) u.mesh_cap = (uint32_t)std::max(0, atoi(e)); /* test aid */
     cl->d_mesh.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.mesh_cap, 1));
     u.mesh_items = (float4 *)cl->d_mesh.p;
-    /* d_cnt words: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [5] convex items, [6] triangles,
+    /* d_cnt words: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [5] convex items, [6] triangles, [7] work counter of k_mesh_traverse,
      * [8+L] alive edges of level L, [32+L] / [48+L] / [64+L] mesh / convex / triangle items of edge level L */
     u.mesh_n = (uint32_t *)cl->d_cnt.p + 4;
     u.conv_cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states), 0x3fffffffu);
@@ -1097,7 +1103,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         cl->stats.n_launches += 1;
         if (c_end < n_cfg) return;
         src.n = n_cfg; src.s_begin = 0;
-        launch_heavy<SrcConfigs, SinkBits>(im.f, src, sink, u, 148 * 16, s);
+        launch_heavy<SrcConfigs, SinkBits>(im.f, src, sink, u, 148 * 16, s, (uint32_t *)cl->d_cnt.p + 7);
         if (ev) CK(cudaEventRecord(ev[1], s));
         k_recheck_items<SrcConfigs, SinkBits><<<148, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());

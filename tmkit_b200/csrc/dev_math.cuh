@@ -733,6 +733,39 @@ template <typename T> struct MeshRef {
     T cx, cy, cz;         /* bounding-sphere centre, mesh-local */
 };
 
+/* triangles are stored 12 values apart (9 used) so that a float triangle is three aligned 16-byte loads,
+ * nodes are 32 bytes: two 16-byte loads */
+#define TMK_TRI_STRIDE 12
+template <typename T> TMK_HD void load_tri(const T *tris, int tri, Vec3<T> &a, Vec3<T> &b, Vec3<T> &c) {
+    const T *tp = tris + TMK_TRI_STRIDE * (size_t)tri;
+    a = mk<T>(tp[0], tp[1], tp[2]);
+    b = mk<T>(tp[3], tp[4], tp[5]);
+    c = mk<T>(tp[6], tp[7], tp[8]);
+}
+#ifdef __CUDA_ARCH__
+template <> __device__ __forceinline__ void load_tri<float>(const float *tris, int tri, Vec3<float> &a, Vec3<float> &b,
+                                                            Vec3<float> &c) {
+    const float4 *t4 = reinterpret_cast<const float4 *>(tris) + 3 * (size_t)tri;
+    const float4 u = __ldg(t4), v = __ldg(t4 + 1), w = __ldg(t4 + 2);
+    a = mk<float>(u.x, u.y, u.z);
+    b = mk<float>(u.w, v.x, v.y);
+    c = mk<float>(v.z, v.w, w.x);
+}
+#endif
+TMK_HD BvhNode load_node(const BvhNode *nodes, int i) {
+#ifdef __CUDA_ARCH__
+    const float4 *n4 = reinterpret_cast<const float4 *>(nodes + i);
+    const float4 u = __ldg(n4), v = __ldg(n4 + 1);
+    BvhNode nd;
+    nd.lo[0] = u.x; nd.lo[1] = u.y; nd.lo[2] = u.z; nd.a = __float_as_int(u.w);
+    nd.hi[0] = v.x; nd.hi[1] = v.y; nd.hi[2] = v.z; nd.b = __float_as_int(v.w);
+    return nd;
+#else
+    return nodes[i];
+#endif
+}
+
+
 /* quick verdict of a triangle (points in S's local frame) against a box / cylinder: SEP by one of
  * the shape's own axes, the triangle's plane normal or (cylinder) the radial direction towards the
  * triangle; HIT when a vertex lies inside the shape by more than the allowance; else NEED. */
@@ -796,12 +829,63 @@ template <typename T>
 TMK_HD int test_mesh_tri_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> &S, const Xf<T> &XS, int tri) {
     Xf<T> m_in_s = xrel(XS, XM);
     Mat3<T> Rms = q2m(m_in_s.r);
-    const T *tp = M.tris + 9 * (size_t)tri;
-    Vec3<T> p0 = mv(Rms, mk<T>(tp[0], tp[1], tp[2])) + m_in_s.v;
-    Vec3<T> p1 = mv(Rms, mk<T>(tp[3], tp[4], tp[5])) + m_in_s.v;
-    Vec3<T> p2 = mv(Rms, mk<T>(tp[6], tp[7], tp[8])) + m_in_s.v;
+    Vec3<T> t0, t1, t2;
+    load_tri(M.tris, tri, t0, t1, t2);
+    Vec3<T> p0 = mv(Rms, t0) + m_in_s.v;
+    Vec3<T> p1 = mv(Rms, t1) + m_in_s.v;
+    Vec3<T> p2 = mv(Rms, t2) + m_in_s.v;
     return test_tri_vs_shape(S, p0, p1, p2);
 }
+
+/* a convex shape S against a mesh, in the mesh frame: what the tree walk needs per query */
+template <typename T> struct MeshQuery {
+    Mat3<T> Rms;       /* mesh frame -> S frame */
+    Vec3<T> tms;       /* ... and its translation */
+    Vec3<T> c;         /* S's centre in the mesh frame */
+    T ex, ey, ez;      /* S's extents along the mesh axes (padded) */
+    T rad2;            /* (bounding radius of S + pad)^2 */
+    TMK_HD void init(const Xf<T> &XM, const Shape<T> &S, const Xf<T> &XS, T s_brad) {
+        Xf<T> s_in_m = xrel(XM, XS); /* S in mesh frame */
+        Xf<T> m_in_s = xrel(XS, XM); /* mesh in S frame */
+        Rms = q2m(m_in_s.r);
+        tms = m_in_s.v;
+        c = s_in_m.v;
+        const T pad = Num<T>::eps() * T(4);
+        T rad = s_brad + pad;
+        rad2 = rad * rad;
+        /* extents of S along the mesh axes (rows of Rms = S's axes in the mesh frame, transposed) */
+        if (S.kind == K_SPHERE) {
+            ex = ey = ez = S.a + pad;
+        } else if (S.kind == K_BOX) {
+            ex = S.a * t_abs(Rms.m00) + S.b * t_abs(Rms.m10) + S.c * t_abs(Rms.m20) + pad;
+            ey = S.a * t_abs(Rms.m01) + S.b * t_abs(Rms.m11) + S.c * t_abs(Rms.m21) + pad;
+            ez = S.a * t_abs(Rms.m02) + S.b * t_abs(Rms.m12) + S.c * t_abs(Rms.m22) + pad;
+        } else { /* cylinder axis in the mesh frame = third row of Rms */
+            const T ux = Rms.m20, uy = Rms.m21, uz = Rms.m22;
+            ex = S.b * t_abs(ux) + S.a * t_sqrt(t_max(T(0), T(1) - ux * ux)) + pad + T(1e-6) * S.a;
+            ey = S.b * t_abs(uy) + S.a * t_sqrt(t_max(T(0), T(1) - uy * uy)) + pad + T(1e-6) * S.a;
+            ez = S.b * t_abs(uz) + S.a * t_sqrt(t_max(T(0), T(1) - uz * uz)) + pad + T(1e-6) * S.a;
+        }
+    }
+    /* S's axis-aligned bounds in the mesh frame against the node, then its bounding sphere */
+    TMK_HD bool overlaps(const BvhNode &nd) const {
+        if (c.x - ex > T(nd.hi[0]) || c.x + ex < T(nd.lo[0]) || c.y - ey > T(nd.hi[1]) || c.y + ey < T(nd.lo[1]) ||
+            c.z - ez > T(nd.hi[2]) || c.z + ez < T(nd.lo[2]))
+            return false;
+        T dx = t_max(t_max(T(nd.lo[0]) - c.x, c.x - T(nd.hi[0])), T(0));
+        T dy = t_max(t_max(T(nd.lo[1]) - c.y, c.y - T(nd.hi[1])), T(0));
+        T dz = t_max(t_max(T(nd.lo[2]) - c.z, c.z - T(nd.hi[2])), T(0));
+        return !(dx * dx + dy * dy + dz * dz > rad2);
+    }
+    /* triangle `tri` of the mesh in S's frame */
+    TMK_HD void tri_in_s(const T *tris, int tri, Vec3<T> &p0, Vec3<T> &p1, Vec3<T> &p2) const {
+        Vec3<T> t0, t1, t2;
+        load_tri(tris, tri, t0, t1, t2);
+        p0 = mv(Rms, t0) + tms;
+        p1 = mv(Rms, t1) + tms;
+        p2 = mv(Rms, t2) + tms;
+    }
+};
 
 /* shape S (sphere/box/cyl, pose XS) against mesh (pose XM) */
 /* UncTri: what to do with a triangle the FP32 tests cannot decide.  NeedTri: what to do with a
@@ -810,47 +894,19 @@ TMK_HD int test_mesh_tri_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape
 template <typename T, class UncTri = NoTri, class NeedTri = NoTri>
 TMK_HD int test_mesh_shape(const MeshRef<T> &M, const Xf<T> &XM, const Shape<T> &S, const Xf<T> &XS, T s_brad,
                            unsigned *n_leaf = nullptr, UncTri on_unc_tri = UncTri(), NeedTri on_need_tri = NeedTri()) {
-    Xf<T> s_in_m = xrel(XM, XS); /* S in mesh frame */
-    Xf<T> m_in_s = xrel(XS, XM); /* mesh in S frame */
-    Mat3<T> Rms = q2m(m_in_s.r);
-    Vec3<T> c = s_in_m.v;
-    const T pad = Num<T>::eps() * T(4);
-    T rad = s_brad + pad;
-    T rad2 = rad * rad;
-    /* extents of S along the mesh axes (rows of Rms = S's axes in the mesh frame, transposed) */
-    T ex, ey, ez;
-    if (S.kind == K_SPHERE) {
-        ex = ey = ez = S.a + pad;
-    } else if (S.kind == K_BOX) {
-        ex = S.a * t_abs(Rms.m00) + S.b * t_abs(Rms.m10) + S.c * t_abs(Rms.m20) + pad;
-        ey = S.a * t_abs(Rms.m01) + S.b * t_abs(Rms.m11) + S.c * t_abs(Rms.m21) + pad;
-        ez = S.a * t_abs(Rms.m02) + S.b * t_abs(Rms.m12) + S.c * t_abs(Rms.m22) + pad;
-    } else { /* cylinder axis in the mesh frame = third row of Rms */
-        const T ux = Rms.m20, uy = Rms.m21, uz = Rms.m22;
-        ex = S.b * t_abs(ux) + S.a * t_sqrt(t_max(T(0), T(1) - ux * ux)) + pad + T(1e-6) * S.a;
-        ey = S.b * t_abs(uy) + S.a * t_sqrt(t_max(T(0), T(1) - uy * uy)) + pad + T(1e-6) * S.a;
-        ez = S.b * t_abs(uz) + S.a * t_sqrt(t_max(T(0), T(1) - uz * uz)) + pad + T(1e-6) * S.a;
-    }
+    MeshQuery<T> Q;
+    Q.init(XM, S, XS, s_brad);
     int stack[32];
     int sp = 0;
     stack[sp++] = 0;
     int result = SEP;
     while (sp > 0) {
-        BvhNode nd = M.nodes[stack[--sp]];
-        /* S's axis-aligned bounds in the mesh frame against the node, then its bounding sphere */
-        if (c.x - ex > T(nd.hi[0]) || c.x + ex < T(nd.lo[0]) || c.y - ey > T(nd.hi[1]) || c.y + ey < T(nd.lo[1]) ||
-            c.z - ez > T(nd.hi[2]) || c.z + ez < T(nd.lo[2]))
-            continue;
-        T dx = t_max(t_max(T(nd.lo[0]) - c.x, c.x - T(nd.hi[0])), T(0));
-        T dy = t_max(t_max(T(nd.lo[1]) - c.y, c.y - T(nd.hi[1])), T(0));
-        T dz = t_max(t_max(T(nd.lo[2]) - c.z, c.z - T(nd.hi[2])), T(0));
-        if (dx * dx + dy * dy + dz * dz > rad2) continue;
+        BvhNode nd = load_node(M.nodes, stack[--sp]);
+        if (!Q.overlaps(nd)) continue;
         if (nd.b > 0) {
             for (int k = 0; k < nd.b; k++) {
-                const T *tp = M.tris + 9 * (size_t)(nd.a + k);
-                Vec3<T> p0 = mv(Rms, mk<T>(tp[0], tp[1], tp[2])) + m_in_s.v;
-                Vec3<T> p1 = mv(Rms, mk<T>(tp[3], tp[4], tp[5])) + m_in_s.v;
-                Vec3<T> p2 = mv(Rms, mk<T>(tp[6], tp[7], tp[8])) + m_in_s.v;
+                Vec3<T> p0, p1, p2;
+                Q.tri_in_s(M.tris, nd.a + k, p0, p1, p2);
                 if (n_leaf) (*n_leaf)++;
                 int r;
                 if (S.kind == K_SPHERE) r = test_tri_vs_shape(S, p0, p1, p2);

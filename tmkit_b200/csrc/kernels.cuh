@@ -124,10 +124,11 @@ __device__ int test_geoms(const DGeom<T> &A, const Xf<T> &XA, const DGeom<T> &B,
             BvhNode na = MA.nodes[stackA[--spA]];
             if (na.b <= 0) { stackA[spA++] = na.a; stackA[spA++] = -na.b - 1; continue; }
             for (int k = 0; k < na.b; k++) {
-                const T *tp = MA.tris + 9 * (size_t)(na.a + k);
-                Vec3<T> a0 = mv(R, mk<T>(tp[0], tp[1], tp[2])) + a_in_b.v;
-                Vec3<T> a1 = mv(R, mk<T>(tp[3], tp[4], tp[5])) + a_in_b.v;
-                Vec3<T> a2 = mv(R, mk<T>(tp[6], tp[7], tp[8])) + a_in_b.v;
+                Vec3<T> ta0, ta1, ta2;
+                load_tri(MA.tris, na.a + k, ta0, ta1, ta2);
+                Vec3<T> a0 = mv(R, ta0) + a_in_b.v;
+                Vec3<T> a1 = mv(R, ta1) + a_in_b.v;
+                Vec3<T> a2 = mv(R, ta2) + a_in_b.v;
                 Vec3<T> c = (a0 + a1 + a2) * T(1.0 / 3.0);
                 T r2 = t_max(dot(a0 - c, a0 - c), t_max(dot(a1 - c, a1 - c), dot(a2 - c, a2 - c)));
                 T rad = t_sqrt(r2);
@@ -141,10 +142,9 @@ __device__ int test_geoms(const DGeom<T> &A, const Xf<T> &XA, const DGeom<T> &B,
                     if (dx * dx + dy * dy + dz * dz > rad * rad) continue;
                     if (nb.b <= 0) { stackB[spB++] = nb.a; stackB[spB++] = -nb.b - 1; continue; }
                     for (int j = 0; j < nb.b; j++) {
-                        const T *tq = MB.tris + 9 * (size_t)(nb.a + j);
-                        if (test_tri_tri(a0, a1, a2, mk<T>(tq[0], tq[1], tq[2]), mk<T>(tq[3], tq[4], tq[5]),
-                                         mk<T>(tq[6], tq[7], tq[8])) == HIT)
-                            return HIT;
+                        Vec3<T> b0, b1, b2;
+                        load_tri(MB.tris, nb.a + j, b0, b1, b2);
+                        if (test_tri_tri(a0, a1, a2, b0, b1, b2) == HIT) return HIT;
                     }
                 }
             }

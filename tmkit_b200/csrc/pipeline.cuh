@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(128) k_conv_items(Image<float> im, Src src, Si
 /* mesh pairs: AABB-tree traversal with the per-triangle certificates; open triangles go to the
  * triangle list */
 template <class Src, class Sink>
-__global__ void __launch_bounds__(128) k_mesh_traverse(Image<float> im, Src src, Sink sink, UncList unc) {
+__global__ void __launch_bounds__(128) k_mesh_traverse_simple(Image<float> im, Src src, Sink sink, UncList unc) {
     uint32_t n = *unc.mesh_n;
     if (n > unc.mesh_cap) n = unc.mesh_cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -640,6 +640,105 @@ __global__ void __launch_bounds__(128) k_mesh_traverse(Image<float> im, Src src,
         const int r = test_geoms(A, h.XA, B, XB, im.meshes, on_unc, on_need);
         if (r == HIT) sink.mark_hit(src.from_id(h.id_x, h.id_y));
         else if (r == UNC) unc_emit(unc, h.id_x, h.id_y, h.key, TMK_WHOLE_PAIR);
+    }
+}
+
+/* The same walk with the lanes kept busy.  One item per thread leaves 5.5 of 32 lanes active per instruction:
+ * most walks end at the root box, a few visit dozens of nodes and test triangles, and a lane in a leaf
+ * (vertex transforms + certificates, ~150 instructions) stalls the lanes that only step through inner nodes
+ * (~30).  Here a warp is a pool of 32 walkers over a shared work counter: idle lanes refill together once
+ * a quarter of the warp is idle, inner-node steps run for every lane that has no leaf pending, and pending
+ * leaves are processed one triangle at a time when enough lanes hold one (or nobody can step). */
+#define TMK_TRAV_STACK 24
+template <class Src, class Sink>
+__global__ void __launch_bounds__(128) k_mesh_traverse(Image<float> im, Src src, Sink sink, UncList unc, uint32_t *next) {
+    __shared__ int stk[TMK_TRAV_STACK][128];
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint32_t n = *unc.mesh_n;
+    if (n > unc.mesh_cap) n = unc.mesh_cap;
+    bool busy = false, exhausted = false, unc_whole = false;
+    uint32_t rec = 0, id_x = 0, id_y = 0, key = 0;
+    const BvhNode *nodes = nullptr;
+    const float *tris = nullptr;
+    Shape<float> S;
+    S.kind = K_SPHERE; S.a = S.b = S.c = 0.f;
+    MeshQuery<float> Q;
+    int sp = 0, leaf_a = 0, leaf_n = 0;
+    for (;;) {
+        unsigned busy_m = __ballot_sync(0xffffffffu, busy);
+        if (!exhausted && __popc(~busy_m) >= 8) {
+            const unsigned idle = ~busy_m;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+            if (!busy) {
+                const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    const HeavyRec h = heavy_load(unc.mesh_items + (size_t)i * TMK_MESH_REC);
+                    rec = i; id_x = h.id_x; id_y = h.id_y; key = h.key;
+                    const DGeom<float> &A = im.mg[ITEM_A(key)];
+                    const DGeom<float> &B = ITEM_STATIC(key) ? im.sg[ITEM_B(key)] : im.mg[ITEM_B(key)];
+                    const Xf<float> XB = ITEM_STATIC(key) ? xload(B.tf) : h.XB;
+                    if (A.shape == K_MESH && B.shape == K_MESH) {
+                        unc_emit(unc, id_x, id_y, key, TMK_WHOLE_PAIR); /* mesh against mesh: exact path only */
+                    } else {
+                        const bool a_mesh = A.shape == K_MESH;
+                        const MeshRef<float> &M = im.meshes[a_mesh ? A.mesh : B.mesh];
+                        nodes = M.nodes; tris = M.tris;
+                        S = shape_of(a_mesh ? B : A);
+                        Q.init(a_mesh ? h.XA : XB, S, a_mesh ? XB : h.XA, a_mesh ? B.brad : A.brad);
+                        stk[0][tid] = 0;
+                        sp = 1; leaf_n = 0; unc_whole = false;
+                        busy = true;
+                    }
+                }
+            }
+            busy_m = __ballot_sync(0xffffffffu, busy);
+        }
+        if (busy_m == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        /* inner steps: every walker without a pending leaf pops nodes until it finds a leaf */
+#pragma unroll 1
+        for (int it = 0; it < 4; it++) {
+            if (busy && leaf_n == 0) {
+                if (sp == 0) {
+                    if (unc_whole) unc_emit(unc, id_x, id_y, key, TMK_WHOLE_PAIR);
+                    busy = false;
+                } else {
+                    const BvhNode nd = load_node(nodes, stk[--sp][tid]);
+                    if (Q.overlaps(nd)) {
+                        if (nd.b > 0) { leaf_a = nd.a; leaf_n = nd.b; }
+                        else if (sp + 2 <= TMK_TRAV_STACK) { stk[sp++][tid] = nd.a; stk[sp++][tid] = -nd.b - 1; }
+                        else unc_whole = true; /* cannot happen for trees built by the host */
+                    }
+                }
+            }
+        }
+        /* leaf step: one triangle for every walker that holds a leaf */
+        const unsigned pend = __ballot_sync(0xffffffffu, busy && leaf_n > 0);
+        const unsigned can_step = __ballot_sync(0xffffffffu, busy && leaf_n == 0);
+        if (pend && (__popc(pend) >= 12 || can_step == 0)) {
+            if (busy && leaf_n > 0) {
+                const int tri = leaf_a;
+                leaf_a++; leaf_n--;
+                Vec3<float> p0, p1, p2;
+                Q.tri_in_s(tris, tri, p0, p1, p2);
+                int r;
+                if (S.kind == K_SPHERE) r = test_tri_vs_shape(S, p0, p1, p2);
+                else r = quick_tri(S, p0, p1, p2);
+                if (r == HIT) {
+                    sink.mark_hit(src.from_id(id_x, id_y));
+                    busy = false; leaf_n = 0;
+                } else if (r == NEED) { /* open triangle: to the triangle list (GJK in k_tri_items) */
+                    const uint32_t k = atomicAdd(unc.tri_n, 1u);
+                    if (k < unc.tri_cap) unc.tri_items[k] = make_uint2(rec, (uint32_t)tri);
+                    else unc_emit(unc, id_x, id_y, key, (uint32_t)tri);
+                } else if (r == UNC) unc_emit(unc, id_x, id_y, key, (uint32_t)tri);
+            }
+        }
     }
 }
 
