@@ -183,3 +183,48 @@ def test_c_executor_replays_the_plan(built, tmp_path):
     for name, pos in final.items():
         np.testing.assert_allclose(pos, ab[orc.frame_id(name)][4:], atol=1e-8)
     assert final["block_a"][2] - final["block_b"][2] == pytest.approx(0.1001, abs=1e-6)
+
+
+def test_workspace_goal_ik_prismatic_chain(built):
+    """the one-launch IK (ik.cuh) on a chain that mixes prismatic and revolute joints with tilted, non-unit axes:
+    goals generated from random configurations must be reached to 1e-6."""
+    sc = S.Scene()
+    sc.add(S.Frame("base", "", S.FIXED, geoms=[S.Geom(S.BOX, (0.2, 0.2, 0.1))]))
+    sc.add(S.Frame("slide", "base", S.PRISMATIC, S.quat_from_rpy(0.1, 0.2, 0.3), (0, 0, 0.2), (1.0, 0, 0), "x", 0.05, (-1, 1)))
+    sc.add(S.Frame("yaw", "slide", S.REVOLUTE, (0, 0, 0, 1), (0, 0, 0.15), (0, 0, 1.0), "a", 0.0, (-3, 3)))
+    sc.add(S.Frame("pitch", "yaw", S.REVOLUTE, S.quat_from_rpy(0.3, 0.0, 0.1), (0.2, 0, 0), (0, 2.0, 0), "b", 0.1, (-2, 2)))
+    sc.add(S.Frame("lift", "pitch", S.PRISMATIC, (0, 0, 0, 1), (0.1, 0, 0), (0, 0.6, 0.8), "z", 0.0, (-0.5, 0.5)))
+    sc.add(S.Frame("roll", "lift", S.REVOLUTE, (0, 0, 0, 1), (0.1, 0, 0), (1.0, 0, 0), "c", 0.0, (-3, 3)))
+    sc.add(S.Frame("wrist", "roll", S.REVOLUTE, (0, 0, 0, 1), (0.1, 0, 0), (0, 1.0, 0), "d", 0.0, (-3, 3)))
+    sc.add(S.Frame("tool", "wrist", S.FIXED, S.quat_from_rpy(0.0, 0.4, 0.0), (0.15, 0, 0.02),
+                   geoms=[S.Geom(S.SPHERE, (0.02, 0, 0))]))
+    sc.allowed = [("base", "tool")]
+    sg = A.SceneGraph.from_scene(sc)
+    names = sg.config_names()
+    q0 = np.zeros(len(names))
+    rng = np.random.default_rng(5)
+    lo = np.array([-1, -3, -2, -0.5, -3, -3.0])
+    hi = -lo
+    order = {n: i for i, n in enumerate(names)}
+    n_found = 0
+    for trial in range(8):
+        q_star = np.zeros(len(names))
+        for n, l, h in zip(["x", "a", "b", "z", "c", "d"], lo, hi):
+            q_star[order[n]] = rng.uniform(0.8 * l, 0.8 * h)
+        _, ab = sg.tf(q_star)
+        goal = ab[sg.frame_id("tool")]
+        ssg = A.SubSceneGraph(sg, "", "tool")
+        mp = A.MotionPlanner(ssg)
+        mp.set_seed(trial)
+        mp.set_start(q0)
+        if mp.set_wsgoal(goal) == 0:
+            continue  # every converged candidate was in collision or none converged: allowed, but rare
+        path = mp.plan(3.0)
+        if path is None:
+            continue
+        n_found += 1
+        _, ab1 = sg.tf(path[-1])
+        tip = ab1[sg.frame_id("tool")]
+        assert np.abs(tip[4:] - goal[4:]).max() < 1e-6
+        assert min(np.abs(tip[:4] - goal[:4]).max(), np.abs(tip[:4] + goal[:4]).max()) < 1e-6
+    assert n_found >= 6, n_found

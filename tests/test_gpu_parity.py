@@ -719,3 +719,38 @@ def test_full_size_edges_properties(gpu_sussman):
         else:
             assert not sv.all(), e
             assert first[e] == int(np.argmin(sv)), e
+
+
+def test_context_churn_recycles_buffers_without_stale_state():
+    """a task-motion planner creates a collision context per motion query; device buffers, pinned slots and
+    streams are recycled through process-wide pools (cl.cu).  Interleave contexts of two scenes of different
+    size and check every one against the oracle: a recycled buffer must never leak state into the next user."""
+    scenes = []
+    for sc in (S.baxter_sussman(), S.blocksworld_scene(16, seed=16)):
+        q0 = S.q0_vector(sc)
+        scenes.append((sc, q0, _oracle_scene(sc, q0)))
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    expected = {}
+    for it in range(12):
+        k = it % 2
+        sc, q0, orc = scenes[k]
+        sg, cl, _ = _gpu_scene(sc, q0)
+        sub = sg.config_indices(S.RIGHT_ARM)
+        n = [700, 33, 4096, 1][it % 4]
+        Q = W.random_configs(lim, n, seed=100 + it % 4)
+        valid = cl.check_batch(sub, q0, Q)
+        key = (k, it % 4)
+        if key not in expected:
+            st, _ = orc.check_batch(orc.config_ids(S.RIGHT_ARM), q0, Q, threads=CORES, early_out=True)
+            _assert_verdicts(valid, st, f"churn {it}", max_band_frac=1.0 if n < 100 else 0.02)
+            expected[key] = valid.copy()
+        else:
+            assert np.array_equal(valid, expected[key]), f"context {it}: verdicts changed on a recycled context"
+        a, b = W.random_edges(lim, 64, seed=it)
+        v1, f1 = cl.check_edges(sub, q0, a, b, W.seg_len(lim))
+        v2, f2 = cl.check_edges(sub, q0, a, b, W.seg_len(lim))  # same arguments: replayed from a CUDA graph
+        v3, f3 = cl.check_edges(sub, q0, a, b, W.seg_len(lim))
+        assert np.array_equal(v1, v2) and np.array_equal(f1, f2) and np.array_equal(v1, v3) and np.array_equal(f1, f3)
+        st = orc.check_edges(orc.config_ids(S.RIGHT_ARM), q0, a, b, W.seg_len(lim), threads=CORES)[0]
+        _assert_verdicts(v1, st, f"churn edges {it}", max_band_frac=0.1)
+        del cl, sg
