@@ -991,6 +991,9 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
                        k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128, false>);
     }
     if (mg.size() > 64) im.wcfg.smem = im.wcfg_e.smem = -1; /* queue items hold a 6-bit moving-geometry index */
+    if (getenv("TMK_DEBUG_IMAGE"))
+        fprintf(stderr, "tmkcl tile: configs TILE %d, %d B shared memory, grid %d | edges TILE %d, %d B, grid %d\n", im.wcfg.tile,
+                im.wcfg.smem, im.wcfg.grid, im.wcfg_e.tile, im.wcfg_e.smem, im.wcfg_e.grid);
     im.valid = true;
     im.serial++;
     hs.mark("tile_configure");
