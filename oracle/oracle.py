@@ -28,6 +28,7 @@ class _Scene(C.Structure):
         ("n_mesh", C.c_int),
         ("mesh_vstart", C.c_void_p), ("mesh_tstart", C.c_void_p), ("verts", C.c_void_p), ("tris", C.c_void_p),
         ("allowed", C.c_void_p),
+        ("mesh_bc", C.c_void_p), ("mesh_br", C.c_void_p), ("tri_c", C.c_void_p), ("tri_b", C.c_void_p),
     ]
 
 
@@ -83,7 +84,10 @@ def _p(a: np.ndarray) -> int:
 class OracleScene:
     """Flat scene arrays (from tmkit_b200.scenes.flatten) held alive for the C side."""
 
-    def __init__(self, flat: Dict[str, np.ndarray], libpath: Optional[str] = None):
+    def __init__(self, flat: Dict[str, np.ndarray], libpath: Optional[str] = None, culls: bool = True):
+        """culls=False leaves the optional bounding-sphere tables out (plain brute force): only used by the test
+        that checks the culls never change a verdict."""
+        self.culls = culls
         self.L = lib(libpath) if libpath else lib()
         self.flat = flat
         self.names = list(flat["names"])
@@ -97,6 +101,28 @@ class OracleScene:
                         ("mesh_tstart", np.int32), ("verts", np.float64), ("tris", np.int32), ("allowed", np.uint8)):
             k[key] = np.ascontiguousarray(flat[key], dtype=dt)
         self.n_g = len(k["g_frame"])
+        # bounding sphere of every mesh in its own frame (centre of the vertex box, farthest vertex): lets the C
+        # side skip triangles whose outcome is FREE anyway - verdicts are unaffected
+        vs, n_mesh = k["mesh_vstart"], len(k["mesh_vstart"]) - 1
+        bc = np.zeros((max(n_mesh, 1), 3))
+        br = np.zeros(max(n_mesh, 1))
+        for m in range(n_mesh):
+            v = k["verts"].reshape(-1, 3)[vs[m]:vs[m + 1]]
+            bc[m] = 0.5 * (v.min(axis=0) + v.max(axis=0))
+            br[m] = np.sqrt(((v - bc[m]) ** 2).sum(axis=1).max()) * (1 + 1e-12)
+        k["mesh_bc"], k["mesh_br"] = np.ascontiguousarray(bc), np.ascontiguousarray(br)
+        # ... and centroid / radius of every triangle in its mesh frame
+        ts = k["mesh_tstart"]
+        tri = k["tris"].reshape(-1, 3)
+        tc = np.zeros((max(len(tri), 1), 3))
+        tb = np.zeros(max(len(tri), 1))
+        for m in range(n_mesh):
+            v = k["verts"].reshape(-1, 3)[vs[m]:vs[m + 1]]
+            p = v[tri[ts[m]:ts[m + 1]]]  # nt x 3 x 3
+            c = p.mean(axis=1)
+            tc[ts[m]:ts[m + 1]] = c
+            tb[ts[m]:ts[m + 1]] = np.sqrt(((p - c[:, None, :]) ** 2).sum(axis=2).max(axis=1)) * (1 + 1e-12)
+        k["tri_c"], k["tri_b"] = np.ascontiguousarray(tc), np.ascontiguousarray(tb)
         self._refresh()
 
     def _refresh(self):
@@ -105,8 +131,10 @@ class OracleScene:
         s.n_f, s.n_q, s.n_g = self.n_f, self.n_q, self.n_g
         s.n_mesh = len(k["mesh_vstart"]) - 1
         for key in ("parent", "type", "E", "axis", "offset", "qidx", "g_frame", "g_shape", "g_dim", "g_mesh",
-                    "mesh_vstart", "mesh_tstart", "verts", "tris", "allowed"):
+                    "mesh_vstart", "mesh_tstart", "verts", "tris", "allowed", "mesh_bc", "mesh_br", "tri_c", "tri_b"):
             setattr(s, key, _p(k[key]))
+        if not self.culls:
+            s.mesh_bc = s.mesh_br = s.tri_c = s.tri_b = None
         self.c = s
 
     @property

@@ -68,6 +68,14 @@ typedef struct {
     const double *verts; /* [nv*3] */
     const int *tris;     /* [nt*3], indices local to the mesh */
     const uint8_t *allowed; /* [n_f*n_f] */
+    /* optional (may be NULL): bounding sphere of every mesh in its own frame - centre [n_mesh*3], radius [n_mesh].
+     * Only used to skip work whose outcome is FREE anyway (the fast mode SURVEY.md 8d asks the CPU baseline to have) */
+    const double *mesh_bc;
+    const double *mesh_br;
+    /* optional: centroid [nt*3] and bounding radius about it [nt] of every triangle in its mesh frame
+     * (rows follow `tris`): triangles are culled there before they are transformed */
+    const double *tri_c;
+    const double *tri_b;
 } orc_scene;
 
 /* ------------------------------------------------------------------ vector / quaternion */
@@ -368,11 +376,12 @@ static void make_tri(const double *tf, const double *R, const double *v0, const 
 }
 
 /* tri-state of one convex pair; *exact = the boolean verdict */
-static int convex_pair(int sa, const double *da, const double *ta, const cvx *triA,
-                       int sb, const double *db, const double *tb, const cvx *triB, double tol, int *exact) {
+static int convex_pair_pre(int sa, const double *da, const double *ta, const cvx *triA, const cvx *preA,
+                           int sb, const double *db, const double *tb, const cvx *triB, const cvx *preB, double tol,
+                           int *exact) {
     cvx A, B;
-    if (triA) A = *triA; else make_cvx(sa, da, ta, &A, 0);
-    if (triB) B = *triB; else make_cvx(sb, db, tb, &B, 0);
+    if (triA) A = *triA; else if (preA) A = *preA; else make_cvx(sa, da, ta, &A, 0);
+    if (triB) B = *triB; else if (preB) B = *preB; else make_cvx(sb, db, tb, &B, 0);
     double d[3];
     sub3(A.c, B.c, d);
     double reach = A.bound + B.bound + tol;
@@ -390,13 +399,31 @@ static int convex_pair(int sa, const double *da, const double *ta, const cvx *tr
     *exact = !gjk_sep(&A, &B, A.rad + B.rad);
     return ORC_BAND;
 }
+static int convex_pair(int sa, const double *da, const double *ta, const cvx *triA,
+                       int sb, const double *db, const double *tb, const cvx *triB, double tol, int *exact) {
+    return convex_pair_pre(sa, da, ta, triA, NULL, sb, db, tb, triB, NULL, tol, exact);
+}
+
+/* world centre of a mesh's bounding sphere */
+static void mesh_centre(const orc_scene *s, int m, const double *tf, const double *R, double *c) {
+    const double *b = s->mesh_bc + 3 * m;
+    for (int i = 0; i < 3; i++) c[i] = tf[4 + i] + R[3 * i] * b[0] + R[3 * i + 1] * b[1] + R[3 * i + 2] * b[2];
+}
+/* spheres (ca, ra), (cb, rb) farther apart than tol: whatever they contain is FREE */
+static int spheres_apart(const double *ca, double ra, const double *cb, double rb, double tol) {
+    double d[3];
+    sub3(ca, cb, d);
+    double reach = ra + rb + tol;
+    return dot3(d, d) > reach * reach;
+}
 
 /* geometry pair (either side may be a mesh = union of triangles) */
-static int geom_pair(const orc_scene *s, int gi, int gj, const double *TF_abs, double tol, int *exact) {
+static int geom_pair(const orc_scene *s, int gi, int gj, const double *TF_abs, double tol, int *exact, const cvx *pre) {
     int si = s->g_shape[gi], sj = s->g_shape[gj];
     const double *ti = TF_abs + 7 * s->g_frame[gi], *tj = TF_abs + 7 * s->g_frame[gj];
     const double *di = s->g_dim + 3 * gi, *dj = s->g_dim + 3 * gj;
-    if (si != ORC_MESH && sj != ORC_MESH) return convex_pair(si, di, ti, NULL, sj, dj, tj, NULL, tol, exact);
+    if (si != ORC_MESH && sj != ORC_MESH)
+        return convex_pair_pre(si, di, ti, NULL, pre ? pre + gi : NULL, sj, dj, tj, NULL, pre ? pre + gj : NULL, tol, exact);
     if (sj != ORC_MESH) { /* put the mesh second */
         int t = gi; gi = gj; gj = t;
         t = si; si = sj; sj = t;
@@ -411,11 +438,29 @@ static int geom_pair(const orc_scene *s, int gi, int gj, const double *TF_abs, d
     const double *vj = s->verts + 3 * s->mesh_vstart[mj];
     const int *fj = s->tris + 3 * s->mesh_tstart[mj];
     int ntj = s->mesh_tstart[mj + 1] - s->mesh_tstart[mj];
+    double cj[3] = {0, 0, 0};
+    if (s->mesh_bc) mesh_centre(s, mj, tj, Rj, cj);
     if (si != ORC_MESH) {
+        cvx A0;
+        if (pre) A0 = pre[gi]; else make_cvx(si, di, ti, &A0, 0);
+        if (s->mesh_bc && spheres_apart(A0.c, A0.bound, cj, s->mesh_br[mj], tol)) return ORC_FREE;
+        /* shape centre in the mesh frame: the cull below is the one convex_pair starts with, moved in front of
+         * the vertex transforms (slack 1e-12 for the change of frame; a triangle that slips through is culled or
+         * decided by convex_pair as before) */
+        double cl[3] = {0, 0, 0};
+        const double *tcj = NULL, *tbj = NULL;
+        if (s->tri_c) {
+            double d0[3] = {A0.c[0] - tj[4], A0.c[1] - tj[5], A0.c[2] - tj[6]};
+            for (int i = 0; i < 3; i++) cl[i] = Rj[i] * d0[0] + Rj[3 + i] * d0[1] + Rj[6 + i] * d0[2];
+            tcj = s->tri_c + 3 * s->mesh_tstart[mj];
+            tbj = s->tri_b + s->mesh_tstart[mj];
+        }
         for (int t = 0; t < ntj; t++) {
+            if (tcj && spheres_apart(cl, A0.bound, tcj + 3 * t, tbj[t], tol + 1e-12)) continue;
             cvx T;
             make_tri(tj, Rj, vj + 3 * fj[3 * t], vj + 3 * fj[3 * t + 1], vj + 3 * fj[3 * t + 2], &T);
-            int st = convex_pair(si, di, ti, NULL, ORC_TRI, NULL, NULL, &T, tol, &ex);
+            if (spheres_apart(A0.c, A0.bound, T.c, T.bound, tol)) continue; /* the cull convex_pair starts with */
+            int st = convex_pair_pre(si, di, ti, NULL, &A0, ORC_TRI, NULL, NULL, &T, NULL, tol, &ex);
             *exact |= ex;
             if (st == ORC_HIT) return ORC_HIT;
             if (st == ORC_BAND) state = ORC_BAND;
@@ -429,12 +474,19 @@ static int geom_pair(const orc_scene *s, int gi, int gj, const double *TF_abs, d
     const double *vi = s->verts + 3 * s->mesh_vstart[mi];
     const int *fi = s->tris + 3 * s->mesh_tstart[mi];
     int nti = s->mesh_tstart[mi + 1] - s->mesh_tstart[mi];
+    if (s->mesh_bc) {
+        double ci[3];
+        mesh_centre(s, mi, ti, Ri, ci);
+        if (spheres_apart(ci, s->mesh_br[mi], cj, s->mesh_br[mj], tol)) return ORC_FREE;
+    }
     for (int a = 0; a < nti; a++) {
         cvx TA;
         make_tri(ti, Ri, vi + 3 * fi[3 * a], vi + 3 * fi[3 * a + 1], vi + 3 * fi[3 * a + 2], &TA);
+        if (s->mesh_bc && spheres_apart(TA.c, TA.bound, cj, s->mesh_br[mj], tol)) continue;
         for (int b = 0; b < ntj; b++) {
             cvx TB;
             make_tri(tj, Rj, vj + 3 * fj[3 * b], vj + 3 * fj[3 * b + 1], vj + 3 * fj[3 * b + 2], &TB);
+            if (spheres_apart(TA.c, TA.bound, TB.c, TB.bound, tol)) continue;
             int st = convex_pair(ORC_TRI, NULL, NULL, &TA, ORC_TRI, NULL, NULL, &TB, tol, &ex);
             *exact |= ex;
             if (st == ORC_HIT) return ORC_HIT;
@@ -466,14 +518,33 @@ int orc_check(const orc_scene *s, const double *TF_abs, double tol, const uint8_
               int early_out, int *exact) {
     int state = ORC_FREE;
     *exact = 0;
+    /* every geometry's world shape once per configuration (not once per pair), and its bounding sphere:
+     * pairs whose spheres are more than tol apart are FREE without looking further */
+    cvx *pre = (cvx *)malloc(sizeof(cvx) * (size_t)(s->n_g > 0 ? s->n_g : 1));
+    for (int i = 0; i < s->n_g; i++) {
+        const double *tf = TF_abs + 7 * s->g_frame[i];
+        if (s->g_shape[i] != ORC_MESH) make_cvx(s->g_shape[i], s->g_dim + 3 * i, tf, &pre[i], 0);
+        else {
+            memset(&pre[i], 0, sizeof(cvx));
+            pre[i].bound = -1; /* unknown */
+            if (s->mesh_bc) {
+                double R[9];
+                quat2mat(tf, R);
+                mesh_centre(s, s->g_mesh[i], tf, R, pre[i].c);
+                pre[i].bound = s->mesh_br[s->g_mesh[i]];
+            }
+        }
+    }
     for (int i = 0; i < s->n_g; i++) {
         int fi = s->g_frame[i];
         for (int j = i + 1; j < s->n_g; j++) {
             int fj = s->g_frame[j];
             if (fi == fj || s->allowed[fi * s->n_f + fj]) continue;
             if (skip && skip[i] && skip[j]) continue;
+            if (pre[i].bound >= 0 && pre[j].bound >= 0 && spheres_apart(pre[i].c, pre[i].bound, pre[j].c, pre[j].bound, tol))
+                continue;
             int ex = 0;
-            int st = geom_pair(s, i, j, TF_abs, tol, &ex);
+            int st = geom_pair(s, i, j, TF_abs, tol, &ex, pre);
             *exact |= ex;
             if (st != ORC_FREE && pairset) {
                 uint8_t *p = pairset + fi * s->n_f + fj, *q = pairset + fj * s->n_f + fi;
@@ -481,10 +552,11 @@ int orc_check(const orc_scene *s, const double *TF_abs, double tol, const uint8_
             }
             if (st == ORC_HIT) {
                 state = ORC_HIT;
-                if (early_out) return state;
+                if (early_out) { free(pre); return state; }
             } else if (st == ORC_BAND && state == ORC_FREE) state = ORC_BAND;
         }
     }
+    free(pre);
     return state;
 }
 
@@ -646,7 +718,7 @@ static void prep_static(const orc_scene *s, job *J, uint8_t *g_static, int hoist
             int fi = s->g_frame[i], fj = s->g_frame[j];
             if (!(g_static[i] && g_static[j]) || fi == fj || s->allowed[fi * s->n_f + fj]) continue;
             int ex = 0;
-            int p = geom_pair(s, i, j, abs_, J->tol, &ex);
+            int p = geom_pair(s, i, j, abs_, J->tol, &ex, NULL);
             J->static_exact |= ex;
             if (p == ORC_HIT) st = ORC_HIT;
             else if (p == ORC_BAND && st == ORC_FREE) st = ORC_BAND;

@@ -320,3 +320,36 @@ def test_edge_semantics(sussman):
     est2, _, first2, nchk2 = orc.check_edges(sub, q0, a, b, seg, early_out=True)
     assert np.array_equal(est2 == O.HIT, est == O.HIT)
     assert (nchk2 <= nchk).all()
+
+
+@pytest.mark.parametrize("which", ["sussman", "blocks"])
+def test_bounding_sphere_culls_never_change_a_verdict(which):
+    """the oracle's fast mode (bounding spheres of geometries, meshes and triangles; shapes built once per
+    configuration) against plain brute force: tri-states, exact verdicts and edge results must be identical."""
+    sc = S.baxter_sussman() if which == "sussman" else S.blocksworld_scene(8, seed=8)
+    flat = S.flatten(sc)
+    q0 = S.q0_vector(sc)
+    fast, brute = O.OracleScene(flat), O.OracleScene(S.flatten(sc), culls=False)
+    for o in (fast, brute):
+        o.allow_config(q0)
+    assert np.array_equal(fast.allowed, brute.allowed)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    sub = fast.config_ids(S.RIGHT_ARM)
+    Q = W.random_configs(lim, 1500, seed=11)
+    cores = os.cpu_count() or 1
+    for early in (False, True):
+        s1, e1 = fast.check_batch(sub, q0, Q, threads=cores, early_out=early)
+        s2, e2 = brute.check_batch(sub, q0, Q, threads=cores, early_out=early)
+        assert np.array_equal(s1, s2) and np.array_equal(e1, e2)
+    a, b = W.random_edges(lim, 150, seed=12)
+    r1 = fast.check_edges(sub, q0, a, b, W.seg_len(lim), threads=cores)
+    r2 = brute.check_edges(sub, q0, a, b, W.seg_len(lim), threads=cores)
+    for x, y in zip(r1, r2):
+        assert np.array_equal(x, y)
+    # full pair sets (aa_rx_cl_check with a collision set) at a few configurations, allowances dropped
+    fresh_fast, fresh_brute = O.OracleScene(S.flatten(sc)), O.OracleScene(S.flatten(sc), culls=False)
+    for c in range(4):
+        q = q0.copy()
+        q[sub] = Q[c]
+        p1, p2 = fresh_fast.check(fresh_fast.fk(q)[1]), fresh_brute.check(fresh_brute.fk(q)[1])
+        assert p1[0] == p2[0] and p1[1] == p2[1] and np.array_equal(p1[2], p2[2])
