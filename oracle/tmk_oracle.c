@@ -32,6 +32,12 @@
  *     HIT           = !gjk_sep(A-, B-, rA- + rB-)   A-,B- = shapes eroded by tol/2
  *     BAND          = neither  (contact band; excluded from bit-exact comparison)
  * where r is the radius of a sphere (its core is a point).
+ *
+ * Fast mode (what bench.py times as the CPU baseline): the scan stops at the first HIT
+ * (early_out), every geometry's world shape is built once per configuration, and bounding spheres - of
+ * geometries, of whole meshes, of single triangles in their mesh frame - skip pairs that are more than tol
+ * apart.  A skipped pair is FREE by construction, so tri-states and verdicts are those of the plain scan
+ * (tests/test_oracle_golden.py compares the two).
  */
 #include <math.h>
 #include <pthread.h>
