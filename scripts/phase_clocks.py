@@ -4,9 +4,11 @@ sys.path.insert(0, '.')
 from tmkit_b200 import amino as A, scenes as S, workloads as W
 import torch
 wl = sys.argv[1] if len(sys.argv) > 1 else "configs"
-sc = S.baxter_sussman() if wl == "configs" else S.blocksworld_scene(32, seed=32)
+sc = {"configs": S.baxter_sussman, "blocks": lambda: S.blocksworld_scene(32, seed=32),
+      "clutter": lambda: S.clutter_scene(512, seed=0)}[wl]()
+names_q = S.RIGHT_ARM + S.LEFT_ARM if wl == "clutter" else S.RIGHT_ARM
 sg = A.SceneGraph.from_scene(sc); q0 = S.q0_vector(sc); sg.allow_config(q0); cl = A.Collision(sg)
-sub = sg.config_indices(S.RIGHT_ARM); lim = W.arm_limit_table(S.RIGHT_ARM)
+sub = sg.config_indices(names_q); lim = W.arm_limit_table(names_q)
 n = 1 << 20
 Q = torch.from_numpy(np.ascontiguousarray(W.random_configs(lim, n, 0).T.astype(np.float32))).cuda()
 bits = torch.zeros(n // 32, dtype=torch.int32, device="cuda")

@@ -819,7 +819,8 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     if (im.h_pairs.size() >= (1u << 27)) tmk_die("batch: too many candidate pairs");
 
     /* large scenes: small static geometry goes into a uniform grid and leaves the pipeline's pair list */
-    const double GRID_RMAX = 0.25, GRID_H = 0.4;
+    const double GRID_RMAX = 0.25;
+    const double GRID_H = getenv("TMK_GRID_H") ? atof(getenv("TMK_GRID_H")) : 0.25; /* cell size (0.2-0.3 measured best on 512 obstacles); env = tuning aid */
     std::vector<uint8_t> gridded(sgv.size(), 0);
     size_t n_gridded = 0;
     for (size_t b = 0; b < sgv.size(); b++)
