@@ -754,3 +754,41 @@ def test_context_churn_recycles_buffers_without_stale_state():
         st = orc.check_edges(orc.config_ids(S.RIGHT_ARM), q0, a, b, W.seg_len(lim), threads=CORES)[0]
         _assert_verdicts(v1, st, f"churn edges {it}", max_band_frac=0.1)
         del cl, sg
+
+
+def test_two_threads_two_contexts():
+    """handles are per-planner, the library is re-entrant across handles (SURVEY.md 8b threading): two host threads,
+    each with its own scene graph and collision context, create / use / destroy contexts concurrently (ctypes
+    releases the GIL inside the C calls) and must see the verdicts a single thread sees."""
+    import threading
+    sc = S.baxter_sussman()
+    q0 = S.q0_vector(sc)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    Qs = [W.random_configs(lim, 20000, seed=50 + k) for k in range(2)]
+    sg0, cl0, _ = _gpu_scene(sc, q0)
+    sub = sg0.config_indices(S.RIGHT_ARM)
+    expect = [cl0.check_batch(sub, q0, Q) for Q in Qs]
+    edges = W.random_edges(lim, 300, seed=3)
+    expect_e = cl0.check_edges(sub, q0, edges[0], edges[1], W.seg_len(lim))
+    errors = []
+
+    def worker(k):
+        try:
+            for it in range(6):
+                sg, cl, _ = _gpu_scene(S.baxter_sussman(), q0)
+                v = cl.check_batch(sub, q0, Qs[k])
+                if not np.array_equal(v, expect[k]):
+                    errors.append(f"thread {k} iteration {it}: batch verdicts differ")
+                ve, fe = cl.check_edges(sub, q0, edges[0], edges[1], W.seg_len(lim))
+                if not (np.array_equal(ve, expect_e[0]) and np.array_equal(fe, expect_e[1])):
+                    errors.append(f"thread {k} iteration {it}: edge results differ")
+                del cl, sg
+        except Exception as ex:  # noqa: BLE001 - reported below
+            errors.append(f"thread {k}: {ex!r}")
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
