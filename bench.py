@@ -358,7 +358,9 @@ def main():
     stream = ts.cuda_stream
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    cs = torch.cuda.Stream(device=dev) if world > 1 else None
+    # high priority: when the persistent tile kernel of the next step and the all-gather of this one are both
+    # pending, the collective gets the first free SMs (it is tiny and everybody waits for it)
+    cs = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     ev_done = [torch.cuda.Event() for _ in range(2)]      # kernels of the step wrote bits2[b]
     ev_gathered = [torch.cuda.Event() for _ in range(2)]  # the all-gather has read bits2[b]
 
