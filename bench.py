@@ -364,17 +364,26 @@ def main():
     ev_done = [torch.cuda.Event() for _ in range(2)]      # kernels of the step wrote bits2[b]
     ev_gathered = [torch.cuda.Event() for _ in range(2)]  # the all-gather has read bits2[b]
 
+    sub_c = np.ascontiguousarray(sub, dtype=np.int32)
+    q0_c = np.ascontiguousarray(q0, dtype=np.float64)
+    sub_ptr, q0_ptr, n_sub_c, n_q_c, seg_c = sub_c.ctypes.data, q0_c.ctypes.data, len(sub_c), len(q0_c), float(seg)
+    ring_ptr = [t.data_ptr() for t in ring]
+    ring1_ptr = [t.data_ptr() for t in ring1]
+    bits_ptr = [t.data_ptr() for t in bits2]
+    c_batch, c_edges = cl.L.aa_rx_cl_check_batch_dev, cl.L.aa_rx_cl_check_edges_dev
+
     def step(i):
         k = i % RING
         b = i & 1 if world > 1 else 0
         out = bits2[b]
         if world > 1:
             ts.wait_event(ev_gathered[b])  # the gather of step i-2 is done with this buffer
+        # the C entry points directly, arguments marshalled once: the loop below has to keep a ~1 ms GPU step fed
         if edges:
-            cl.check_edges_dev(n_units, sub, q0, ring[k].data_ptr(), ring1[k].data_ptr(), A.Q_SOA_F32, n_units, seg,
-                               out.data_ptr(), 0, stream)
+            c_edges(cl.h, n_units, n_sub_c, sub_ptr, n_q_c, q0_ptr, ring_ptr[k], ring1_ptr[k], A.Q_SOA_F32, n_units, seg_c,
+                    bits_ptr[b], None, stream)
         else:
-            cl.check_batch_dev(n_units, sub, q0, ring[k].data_ptr(), A.Q_SOA_F32, n_units, out.data_ptr(), stream)
+            c_batch(cl.h, n_units, n_sub_c, sub_ptr, n_q_c, q0_ptr, ring_ptr[k], A.Q_SOA_F32, n_units, bits_ptr[b], stream)
         if world > 1:
             ev_done[b].record(ts)
             cs.wait_event(ev_done[b])
@@ -414,7 +423,7 @@ def main():
         t_host = time.perf_counter()
         for i in range(args.steps):
             step(n_warm + i)
-            if rank == 0 and i % 16 == 8:
+            if rank == 0 and i % 64 == 8:
                 sampler.sample_now()  # while the GPU is busy with the steps already queued
         drain()
         ev[1].record(ts)

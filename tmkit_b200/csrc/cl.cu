@@ -1058,7 +1058,7 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     if (const char *e = getenv("TMK_MESH_CAP")) u.mesh_cap = (uint32_t)std::max(0, atoi(e)); /* test aid */
     cl->d_mesh.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.mesh_cap, 1));
     u.mesh_items = (float4 *)cl->d_mesh.p;
-    /* d_cnt words: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [5] convex items, [6] triangles, [7] work counter of k_mesh_traverse,
+    /* d_cnt words: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [5] convex items, [6] triangles, [7] work counter of k_mesh_traverse, [26..27] tile counter of k_states_tile,
      * [8+L] alive edges of level L, [32+L] / [48+L] / [64+L] mesh / convex / triangle items of edge level L */
     u.mesh_n = (uint32_t *)cl->d_cnt.p + 4;
     u.conv_cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states), 0x3fffffffu);
@@ -1070,6 +1070,7 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     u.conv_n = (uint32_t *)cl->d_cnt.p + 5;
     u.tri_items = (uint2 *)cl->d_tri.p;
     u.tri_n = (uint32_t *)cl->d_cnt.p + 6;
+    u.tile_ctr = (uint32_t *)cl->d_cnt.p + 26; /* words 26, 27 */
     if (reset) CK(cudaMemsetAsync(cl->d_cnt.p, 0, 512, s)); /* after every allocation: capturable */
     return u;
 }

@@ -98,6 +98,7 @@ struct UncList {
     uint2 *tri_items;   /* (mesh record, triangle) the per-triangle certificates left open */
     uint32_t *tri_n;
     uint32_t tri_cap;
+    uint32_t *tile_ctr; /* [0] next tile of the running k_states_tile launch, [1] CTAs that finished it */
 };
 #define TMK_MESH_REC 5 /* float4 per exported mesh item: (id_x, id_y, key, -) poseA[7] - poseB[7] - */
 #define TMK_WHOLE_PAIR 0xffffffffu
@@ -336,7 +337,15 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
 #ifdef TMK_PHASE_CLOCKS
     long long t_phase = clock64();
 #endif
-    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    /* tiles are handed out through a counter, not by CTA index: a CTA that becomes resident late (another
+     * kernel - a collective on a second stream - still holds its SM) then simply takes fewer tiles instead
+     * of stretching the launch by its delay */
+    __shared__ uint32_t s_tile;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(unc.tile_ctr, 1u);
+        __syncthreads();
+        const size_t tile = s_tile;
+        if (tile >= n_tiles) break;
         const size_t s = tile * TILE + tid;
         const typename Src::State st = src.prepare(s);
         const bool live = st.live && !im.static_hit;
@@ -588,6 +597,15 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         sink.emit(st, tile * (TILE / 32) + warp, f_hit[tid] != 0 || !st.live, lane);
         __syncthreads();
         PHASE_MARK(5);
+    }
+    /* the last CTA out re-arms the counter for the next launch of the batch (launches are stream-ordered) */
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(unc.tile_ctr + 1, 1u) == gridDim.x - 1) {
+            unc.tile_ctr[0] = 0;
+            unc.tile_ctr[1] = 0;
+            __threadfence();
+        }
     }
 }
 
