@@ -483,6 +483,20 @@ def main():
     e2e_value = n_units * world * e2e_steps / float(t.item())
     h2d = n_units * len(sub) * 8 * (2 if edges else 1)
     d2h = nw * 4
+    # beside it (information only): the same blocking call with float rows - half the PCIe bytes, which is what
+    # bounds the double-row call (the reference-facing one quoted as `e2e`)
+    e2e_f32 = None
+    if not edges and world == 1:
+        rows32 = [torch.from_numpy(np.ascontiguousarray(h.numpy().astype(np.float32))).pin_memory() for h in host_rows]
+        def f32_step(i):
+            cl.L.aa_rx_cl_check_batch_f32(cl.h, n_units, len(sub), sub.ctypes.data, len(q0), q0.ctypes.data,
+                                          rows32[i % len(rows32)].data_ptr(), len(sub), hb.ctypes.data)
+        for i in range(3):
+            f32_step(i)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            f32_step(i)
+        e2e_f32 = n_units * e2e_steps / (time.perf_counter() - t0)
 
     # ---- untimed runs for the counters: the production path (launches, states it evaluates, pairs it
     # re-checks in double) and the instrumented path (narrowphase calls by class for the flop formula) ----
@@ -539,7 +553,8 @@ def main():
             ", one NCCL all-gather of the validity words per step on a second stream (overlaps the next step; "
             "all gathers finish inside the timed region)" if world > 1 else "")),
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "aa_rx_cl_check_edges" if edges else "aa_rx_cl_check_batch", "host_dtype": "f64 rows, pinned"},
+                "call": "aa_rx_cl_check_edges" if edges else "aa_rx_cl_check_batch", "host_dtype": "f64 rows, pinned",
+                "value_f32_rows": e2e_f32},
         "gpu_launches": int(launches_per_step * args.steps),
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "per_rank_ms": per_rank,  # [step, kernels, host enqueue] per rank

@@ -1305,11 +1305,15 @@ static void stats_end(struct aa_rx_cl *cl, size_t n_units, cudaStream_t s) {
 
 static size_t count_invalid(const uint32_t *bits, size_t n) {
     size_t valid = 0;
-    for (size_t w = 0; w < (n + 31) / 32; w++) {
-        uint32_t x = bits[w];
-        if (w == n / 32 && (n & 31)) x &= (1u << (n & 31)) - 1;
-        valid += (size_t)__builtin_popcount(x);
+    const size_t full = n / 32; /* whole words */
+    size_t w = 0;
+    for (; w + 2 <= full; w += 2) { /* 64 bits at a time (the caller's buffer need not be 8-byte aligned) */
+        uint64_t x;
+        memcpy(&x, bits + w, sizeof(x));
+        valid += (size_t)__builtin_popcountll(x);
     }
+    for (; w < full; w++) valid += (size_t)__builtin_popcount(bits[w]);
+    if (n & 31) valid += (size_t)__builtin_popcount(bits[full] & ((1u << (n & 31)) - 1));
     return n - valid;
 }
 
@@ -1317,6 +1321,7 @@ static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, 
                                size_t n_q, const double *q_base, const void *Q, int layout, size_t ldQ,
                                uint32_t *valid_bits) {
     if (ldQ < n_sub) tmk_die("batch: ldQ < n_sub");
+    HostSpan hs("check_batch_host");
     ensure_image(cl, n_sub, sub_ids, n_q, q_base);
     stats_begin(cl);
     size_t esz = layout == TMK_Q_ROWS_F64 ? 8 : 4;
@@ -1333,8 +1338,11 @@ static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, 
         /* software pipeline: the copy of chunk k+1 (copy stream) overlaps the kernel of chunk k */
         size_t k = 0;
         for (size_t off = 0; off < n_cfg; k++) {
-            size_t end = off + CH;
-            if (end + CH / 2 > n_cfg) end = n_cfg; /* fold a short tail into the last chunk */
+            /* two waves per chunk, one wave towards the end: what runs after the last copy is the last
+             * chunk's kernel, so that chunk is kept short (the copy, not the kernels, sets the pace) */
+            const size_t rem = n_cfg - off;
+            size_t end = off + (rem > 3 * wave ? CH : wave);
+            if (end + wave / 2 > n_cfg) end = n_cfg; /* fold a short tail into the last chunk */
             CK(cudaMemcpyAsync((char *)cl->d_q.p + off * ldQ * esz, (const char *)Q + off * ldQ * esz, (end - off) * ldQ * esz,
                                cudaMemcpyHostToDevice, cl->copy_stream));
             CK(cudaEventRecord(cl->ev_copy[k & 7], cl->copy_stream));
@@ -1344,9 +1352,12 @@ static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, 
         }
     }
     if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
+    hs.mark("enqueued");
     stats_end(cl, n_cfg, cl->stream);
+    hs.mark("synchronised");
     size_t bad = count_invalid(valid_bits, n_cfg);
     cl->stats.n_invalid = bad;
+    hs.mark("counted");
     return bad;
 }
 
