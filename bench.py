@@ -404,9 +404,9 @@ def main():
 
     with torch.cuda.stream(ts):
         l2_flush.zero_()
-        # the swept-edge entry point captures a CUDA graph the second time it sees the same arguments: the
+        # the device-pointer entry points capture a CUDA graph the second time they see the same arguments: the
         # untimed warm-up goes twice around the ring so that the timed steps replay graphs (steady state)
-        n_warm = max(args.warmup, 2 * RING) if edges else args.warmup
+        n_warm = max(args.warmup, 2 * RING)
         for i in range(n_warm):
             step(i)
         barrier()
@@ -414,9 +414,9 @@ def main():
         if rank == 0:
             sampler.start()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        # events around the dominant kernel, recorded by the library on `stream`.  The swept-edge pipeline is
-        # replayed from a CUDA graph (no events inside a graph): its kernel times come from a second, untimed loop
-        inline_timing = not edges
+        # events around the dominant kernel, recorded by the library on `stream`.  The timed steps are
+        # replayed from CUDA graphs (no events inside a graph): the kernel times come from a second, untimed loop
+        inline_timing = False
         cl.kernel_timing(inline_timing)
         barrier()
         ev[0].record(ts)

@@ -1092,6 +1092,36 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         /* fast path: FP32 tile pipeline, then the exact re-check of the undecided pairs.  chunk_* let the
          * host-buffer entry point run the pipeline chunk by chunk behind the copies (one undecided list
          * and one re-check for the whole batch) */
+        /* a whole (unchunked) batch with arguments seen before is replayed from a CUDA graph, like the swept
+         * edges: one driver call per batch keeps a ~1 ms step fed from a busy host */
+        const bool whole = chunk_begin == 0 && (chunk_end == 0 || chunk_end == n_cfg);
+        bool use_graph = whole && n_cfg > 0 && !cl->timing && !getenv("TMK_NO_GRAPH");
+        uint64_t key[12];
+        if (use_graph) {
+            UncList u0 = unc_list(cl, n_cfg, s, false); /* allocations happen outside the capture */
+            (void)u0;
+            const uint64_t k0[12] = {(uint64_t)n_cfg | (1ull << 62), (uint64_t)(uintptr_t)dQ, 0, (uint64_t)layout * 1315423911u + ld, 0,
+                                     (uint64_t)(uintptr_t)d_bits, 0, (uint64_t)(uintptr_t)s, im.serial,
+                                     (uint64_t)(uintptr_t)cl->d_unc.p ^ ((uint64_t)(uintptr_t)cl->d_mesh.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_conv.p << 2),
+                                     0, (uint64_t)(uintptr_t)cl->d_spill.p ^ ((uint64_t)(uintptr_t)cl->d_tri.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_cnt.p << 2)};
+            memcpy(key, k0, sizeof(key));
+            for (auto &g : cl->edge_graphs)
+                if (0 == memcmp(g.key, key, sizeof(key))) {
+                    g.used = ++cl->graph_clock;
+                    CK(cudaGraphLaunch(g.exec, s));
+                    cl->stats.n_launches += g.n_kernels;
+                    return;
+                }
+            bool seen = false;
+            for (auto &k : cl->edge_seen) seen |= 0 == memcmp(k.data(), key, sizeof(key));
+            if (!seen) {
+                std::array<uint64_t, 12> k;
+                memcpy(k.data(), key, sizeof(key));
+                if (cl->edge_seen.size() >= 32) cl->edge_seen.erase(cl->edge_seen.begin());
+                cl->edge_seen.push_back(k);
+                use_graph = false;
+            } else CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        }
         if (chunk_begin == 0) cl->cur_unc = unc_list(cl, n_cfg, s);
         UncList u = cl->cur_unc;
         if (n_cfg == 0) return;
@@ -1116,6 +1146,24 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         CK(cudaGetLastError());
         if (ev) CK(cudaEventRecord(ev[2], s));
         cl->stats.n_launches += 5;
+        if (use_graph) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamEndCapture(s, &graph));
+            aa_rx_cl::EdgeGraph g;
+            memcpy(g.key, key, sizeof(key));
+            CK(cudaGraphInstantiate(&g.exec, graph, 0));
+            CK(cudaGraphDestroy(graph));
+            g.used = ++cl->graph_clock;
+            g.n_kernels = 6;
+            if (cl->edge_graphs.size() >= 16) { /* replace the least recently used */
+                size_t lru = 0;
+                for (size_t k = 1; k < cl->edge_graphs.size(); k++)
+                    if (cl->edge_graphs[k].used < cl->edge_graphs[lru].used) lru = k;
+                cudaGraphExecDestroy(cl->edge_graphs[lru].exec);
+                cl->edge_graphs[lru] = g;
+            } else cl->edge_graphs.push_back(g);
+            CK(cudaGraphLaunch(g.exec, s));
+        }
         return;
     }
     if (chunk_begin != 0 || (chunk_end && chunk_end < n_cfg)) tmk_die("internal: chunked launch on the instrumented path");
