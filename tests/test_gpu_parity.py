@@ -792,3 +792,45 @@ def test_two_threads_two_contexts():
     for t in th:
         t.join()
     assert not errors, errors
+
+
+def test_device_pointer_calls_inside_a_callers_cuda_graph(gpu_sussman):
+    """the asynchronous entry points only enqueue work on the given stream, so a caller can
+    capture them into a CUDA graph of its own (the library then skips its own graph cache) and replay it."""
+    import torch
+    sc, orc, sg, cl, q0 = gpu_sussman
+    sub = sg.config_indices(S.RIGHT_ARM)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    n = 40000
+    Q = W.random_configs(lim, n, seed=77)
+    expect = cl.check_batch(sub, q0, Q)
+    a, b = W.random_edges(lim, 2000, seed=78)
+    exp_v, exp_f = cl.check_edges(sub, q0, a, b, W.seg_len(lim))
+    dq = torch.from_numpy(np.ascontiguousarray(Q.T.astype(np.float32))).cuda()
+    da = torch.from_numpy(np.ascontiguousarray(a.T.astype(np.float32))).cuda()
+    db = torch.from_numpy(np.ascontiguousarray(b.T.astype(np.float32))).cuda()
+    bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    ebits = torch.zeros((2000 + 31) // 32, dtype=torch.int32, device="cuda")
+    efirst = torch.zeros(2000, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+
+    def calls():
+        cl.check_batch_dev(n, sub, q0, dq.data_ptr(), A.Q_SOA_F32, n, bits.data_ptr(), s.cuda_stream)
+        cl.check_edges_dev(2000, sub, q0, da.data_ptr(), db.data_ptr(), A.Q_SOA_F32, 2000, W.seg_len(lim),
+                           ebits.data_ptr(), efirst.data_ptr(), s.cuda_stream)
+
+    with torch.cuda.stream(s):
+        calls()  # warm-up: scratch buffers of these sizes exist afterwards
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s, capture_error_mode="relaxed"):
+            calls()
+        for _ in range(3):
+            bits.zero_(); ebits.zero_(); efirst.zero_()
+            g.replay()
+            s.synchronize()
+            got = np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+            assert np.array_equal(got, expect)
+            gv = np.unpackbits(ebits.cpu().numpy().view(np.uint8), bitorder="little")[:2000].astype(bool)
+            assert np.array_equal(gv, exp_v)
+            assert np.array_equal(efirst.cpu().numpy(), exp_f)

@@ -1075,6 +1075,13 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     return u;
 }
 
+/* the caller may be capturing the stream into a graph of its own: then no nested capture / replay */
+static bool stream_is_capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 /* dQ / d_bits address the whole batch of n_cfg configurations; [chunk_begin, chunk_end) is the part this
  * call evaluates (chunk_end == 0: all of it).  Chunks must be issued in order on the same stream. */
 static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, int layout, size_t ld,
@@ -1095,7 +1102,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         /* a whole (unchunked) batch with arguments seen before is replayed from a CUDA graph, like the swept
          * edges: one driver call per batch keeps a ~1 ms step fed from a busy host */
         const bool whole = chunk_begin == 0 && (chunk_end == 0 || chunk_end == n_cfg);
-        bool use_graph = whole && n_cfg > 0 && !cl->timing && !getenv("TMK_NO_GRAPH");
+        bool use_graph = whole && n_cfg > 0 && !cl->timing && !getenv("TMK_NO_GRAPH") && !stream_is_capturing(s);
         uint64_t key[12];
         if (use_graph) {
             UncList u0 = unc_list(cl, n_cfg, s, false); /* allocations happen outside the capture */
@@ -1205,7 +1212,7 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         cl->d_efirst.need(sizeof(int32_t) * n_edge);
         cl->d_alive0.need(sizeof(uint32_t) * n_edge);
         cl->d_alive1.need(sizeof(uint32_t) * n_edge);
-        bool use_graph = !cl->timing && !getenv("TMK_NO_GRAPH");
+        bool use_graph = !cl->timing && !getenv("TMK_NO_GRAPH") && !stream_is_capturing(s);
         uint64_t key[12] = {(uint64_t)n_edge | ((uint64_t)n_levels << 40), (uint64_t)(uintptr_t)dQ0, (uint64_t)(uintptr_t)dQ1, (uint64_t)layout * 1315423911u + ld,
                             0, (uint64_t)(uintptr_t)d_bits, (uint64_t)(uintptr_t)d_first, (uint64_t)(uintptr_t)s, im.serial,
                             (uint64_t)(uintptr_t)cl->d_unc.p ^ ((uint64_t)(uintptr_t)cl->d_mesh.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_conv.p << 2),
