@@ -47,6 +47,10 @@ int h_convex_f32_iters(int sa, const double *da, const double *ta, int sb, const
     *iters = 0;
     return test_convex(shape_of<float>(sa, da), xf_of<float>(ta), shape_of<float>(sb, db), xf_of<float>(tb), iters);
 }
+int h_convex_f64_iters(int sa, const double *da, const double *ta, int sb, const double *db, const double *tb, int *iters) {
+    *iters = 0;
+    return test_convex(shape_of<double>(sa, da), xf_of<double>(ta), shape_of<double>(sb, db), xf_of<double>(tb), iters);
+}
 int h_quick_tri_f32(int s, const double *d, const double *tri) {
     return quick_tri(shape_of<float>(s, d), mk<float>((float)tri[0], (float)tri[1], (float)tri[2]),
                      mk<float>((float)tri[3], (float)tri[4], (float)tri[5]), mk<float>((float)tri[6], (float)tri[7], (float)tri[8]));

@@ -808,7 +808,16 @@ template <class Src, class Sink>
 __global__ void __launch_bounds__(128) k_recheck_items(Image<double> im, Src src, Sink sink, UncList unc) {
     uint32_t n = *unc.n;
     if (n > unc.cap) n = unc.cap;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    /* The list is short (about a thousand items per 2^20 states) and every item takes its own path through the
+     * double-precision code (GJK of different shapes, iteration counts, triangles): 32 of them in one warp run
+     * one after the other.  So the items are spread as thinly as the grid allows - one per warp when there are
+     * fewer items than warps - and only packed when the list is long. */
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t warp_g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const uint32_t ipw = min(32u, (n + n_warps - 1) / n_warps); /* items per warp and round */
+    for (uint32_t base = warp_g * ipw; base < n; base += n_warps * ipw) {
+        const uint32_t i = base + lane;
+        if (lane >= ipw || i >= n) continue;
         const uint4 it = unc.items[i];
         const uint32_t pair = it.z;
         const typename Src::State st = src.from_id(it.x, it.y);
