@@ -1147,7 +1147,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         src.n = n_cfg; src.s_begin = 0;
         launch_heavy<SrcConfigs, SinkBits>(im.f, src, sink, u, 148 * 16, s, (uint32_t *)cl->d_cnt.p + 7);
         if (ev) CK(cudaEventRecord(ev[1], s));
-        k_recheck_items<SrcConfigs, SinkBits><<<148 * 8, 128, 0, s>>>(im.d, src, sink, u);
+        k_recheck_items<SrcConfigs, SinkBits><<<148 * 3, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         k_overflow_all<SrcConfigs, SinkBits><<<148 * 2, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
@@ -1284,7 +1284,7 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         if (ev) CK(cudaEventRecord(ev[1], s));
         /* undecided (state, pair) items of all levels, in double; positions merge through atomicMin */
         src.alive = nullptr; src.n_alive = nullptr; src.level = 0;
-        k_recheck_items<SrcEdgeLevel, SinkEdgeFirst><<<148 * 8, 128, 0, s>>>(im.d, src, sink, u);
+        k_recheck_items<SrcEdgeLevel, SinkEdgeFirst><<<148 * 3, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());
         k_edges_overflow_all<<<148 * 2, 128, 0, s>>>(im.d, src, u, first);
         CK(cudaGetLastError());
