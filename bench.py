@@ -9,7 +9,13 @@ host-buffer C-ABI call (aa_rx_cl_check_batch) with the H2D / D2H copies inside t
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload configs|edges]
 
 N > 1 is launched by torchrun (one rank per GPU); every rank checks its own batch (weak scaling)
-and the validity bitmaps are all-gathered over NCCL inside the timed region.
+and the validity bitmaps are all-gathered over NCCL inside the timed region (second stream, overlapping
+the next step; the timed stream waits for the last gathers before the closing event).
+
+The timed steps call the asynchronous device-pointer entry points, which replay a CUDA graph for arguments
+they have seen before (the untimed warm-up goes twice around the ring of input batches); the per-kernel
+times in `roofline` come from a second, event-instrumented loop.  `cpu_baseline` / `--impl reference` time
+the oracle's fast mode (oracle/) on the host cores - the only use of oracle/ here.
 """
 from __future__ import annotations
 
