@@ -199,20 +199,55 @@ def cpu_baseline(workload: str, seconds_budget: float = 12.0):
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement on all host cores, exactly K timed steps after W warm-up steps, each
+    step a bounded sample of the workload (the whole run is sized to about two minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    unit = "configs/s" if args.workload == "configs" else "edges/s"
-    vals = []
-    sample = ""
-    cores = 1
-    for _ in range(max(1, min(args.steps, 3))):
-        v, cores, sample, n, dt = cpu_baseline(args.workload, seconds_budget=8.0)
-        vals.append(v)
-    v = float(np.median(vals))
+    from oracle import oracle as O
+    sc, S, W, _, names, n_units_w, kind, _ = make_problem(args.workload)
+    try:
+        path = O.build(force=True, march_native=True, out="/tmp/libtmkoracle_native.so")
+    except Exception:
+        path = O.build()
+    orc = O.OracleScene(S.flatten(sc), libpath=path)
+    q0 = np.asarray([S.Q0.get(n, 0.0) for n in orc.config_names])
+    orc.allow_config(q0)
+    sub = orc.config_ids(names)
+    lim = W.arm_limit_table(names)
+    cores = os.cpu_count() or 1
+    edges = kind == "edges"
+    unit = "edges/s" if edges else "configs/s"
+
+    def make(n, seed):
+        return W.random_edges(lim, n, seed=seed) if edges else (W.random_configs(lim, n, seed=seed),)
+
+    def run(batch):
+        t0 = time.perf_counter()
+        if edges:
+            orc.check_edges(sub, q0, batch[0], batch[1], W.seg_len(lim), early_out=True, threads=cores)
+        else:
+            orc.check_batch(sub, q0, batch[0], early_out=True, threads=cores)
+        return time.perf_counter() - t0
+
+    n_cal = 2000 if edges else 4000
+    rate = n_cal / max(run(make(n_cal, 0)), 1e-6)                      # calibration
+    budget = min(8.0, max(0.25, 120.0 / max(1, args.steps)))           # seconds per step
+    if os.environ.get("TMK_BENCH_REF_BUDGET"):                        # test aid
+        budget = float(os.environ["TMK_BENCH_REF_BUDGET"])
+    n_step = int(max(n_cal, min(200_000 if edges else 4_000_000, rate * budget)))
+    ring = [make(n_step, 1 + r) for r in range(2)]
+    for w in range(args.warmup):
+        run(ring[w % 2])
+    times = [run(ring[i % 2]) for i in range(args.steps)]
+    total = float(sum(times))
+    v = n_step * args.steps / total
+    sample = (f"{n_step} of {n_units_w} {'RRT-like edges' if edges else 'configurations'} per step, early-out, "
+              f"bounding-sphere culls, all cores")
     line = {
-        "impl": "reference", "sample_units": n, "sample_s": dt, "metric": metric_name(args.workload), "value": v, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "impl": "reference", "sample_units": n_step, "sample_s": total / args.steps, "metric": metric_name(args.workload),
+        "value": v, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args.workload),
         "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
