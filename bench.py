@@ -464,11 +464,14 @@ def main():
         t_host = time.perf_counter()
         for i in range(args.steps):
             step(n_warm + i)
-            if rank == 0 and i % 64 == 8:
-                sampler.sample_now()  # while the GPU is busy with the steps already queued
         drain()
         ev[1].record(ts)
         host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps
+        if rank == 0:
+            # graph replays put the host far ahead of the GPU: the clocks are sampled now, with everything
+            # enqueued and the GPU still working through the timed steps (an NVML query inside the loop would
+            # stall the enqueueing thread for milliseconds)
+            sampler.sample_now()
         barrier()
         ms_total = ev[0].elapsed_time(ev[1])
         if not inline_timing:
