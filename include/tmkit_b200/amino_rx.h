@@ -19,7 +19,10 @@
  *   - misuse aborts with a message on stderr (Amino asserts); there is no errno;
  *   - every compute entry point runs on the current CUDA device.  There is NO CPU
  *     fallback: without a usable device the call prints the CUDA error and aborts.
- *   - a handle is used by one thread at a time; distinct handles are independent.
+ *   - a handle is used by one thread at a time; distinct handles are independent.  A collision context lives
+ *     on the device that was current at aa_rx_cl_create and may have work in flight on ONE stream at a time
+ *     (its scratch buffers are per handle): synchronise before switching streams or calling a blocking entry
+ *     point after an asynchronous one.
  */
 #ifndef TMKIT_B200_AMINO_RX_H
 #define TMKIT_B200_AMINO_RX_H
@@ -186,6 +189,85 @@ void aa_rx_cl_check_edges_dev(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, 
                               size_t ld, double seg_len, uint32_t *d_valid_bits, int32_t *d_first_invalid,
                               void *stream);
 void aa_rx_cl_sync(struct aa_rx_cl *cl, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU (new; SURVEY.md 8e, BASELINE.json configs[4]).  The path shards: every GPU holds a replica of
+ * the scene image and checks one contiguous slice of the batch; slices are multiples of TMK_SHARD_ALIGN
+ * units, so every GPU owns whole words of the validity bitmap.  Only the bitmap is exchanged.
+ * The reference's caller is one single-threaded planner with one handle (lisp/python/tmsmtpy.lisp:55-60,
+ * demo/tmpexec.c:397-399): struct aa_rx_cl_multi is that one handle over all GPUs of the box.
+ * ------------------------------------------------------------------------------------- */
+#define TMK_SHARD_ALIGN 1024
+#define TMK_SHARD_ID_BYTES 128
+/* slice of rank `rank` among `world`: units [lo, hi) of [0, n); tmk_shard_words = words per rank in the gathered
+ * bitmap (the gathered bitmap has world * tmk_shard_words(n, world) words; the first ceil(n/32) are the result) */
+size_t tmk_shard_per_rank(size_t n, int world);
+void tmk_shard_bounds(size_t n, int world, int rank, size_t *lo, size_t *hi);
+size_t tmk_shard_words(size_t n, int world);
+
+/* (1) one process, several devices.  devices == NULL: 0 .. n_dev-1; n_dev <= 0: all visible devices.
+ * The per-device contexts are ordinary aa_rx_cl handles (aa_rx_cl_multi_context) living on their device. */
+struct aa_rx_cl_multi;
+struct aa_rx_cl_multi *aa_rx_cl_multi_create(const struct aa_rx_sg *sg, int n_dev, const int *devices);
+void aa_rx_cl_multi_destroy(struct aa_rx_cl_multi *m);
+int aa_rx_cl_multi_device_count(const struct aa_rx_cl_multi *m);
+int aa_rx_cl_multi_device(const struct aa_rx_cl_multi *m, int k);
+struct aa_rx_cl *aa_rx_cl_multi_context(struct aa_rx_cl_multi *m, int k);
+void aa_rx_cl_multi_allow(struct aa_rx_cl_multi *m, aa_rx_frame_id id0, aa_rx_frame_id id1, int allowed);
+void aa_rx_cl_multi_allow_set(struct aa_rx_cl_multi *m, const struct aa_rx_cl_set *set);
+void aa_rx_cl_multi_allow_name(struct aa_rx_cl_multi *m, const char *frame0, const char *frame1, int allowed);
+void aa_rx_cl_multi_track_collisions(struct aa_rx_cl_multi *m, int enable);
+void aa_rx_cl_multi_batch_collisions(struct aa_rx_cl_multi *m, struct aa_rx_cl_set *set);
+/* host buffers, blocking; same arguments and results as the single-device calls.  Every device copies its
+ * slice of the rows in and its words straight into valid_bits (no collective). */
+size_t aa_rx_cl_check_batch_multi(struct aa_rx_cl_multi *m, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                  size_t n_q, const double *q_all_base, const double *Q_sub, size_t ldQ,
+                                  uint32_t *valid_bits);
+size_t aa_rx_cl_check_batch_multi_f32(struct aa_rx_cl_multi *m, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                      size_t n_q, const double *q_all_base, const float *Q_sub, size_t ldQ,
+                                      uint32_t *valid_bits);
+size_t aa_rx_cl_check_edges_multi(struct aa_rx_cl_multi *m, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                  size_t n_q, const double *q_all_base, const double *Q0, const double *Q1, size_t ldQ,
+                                  double seg_len, uint32_t *valid_bits, int32_t *first_invalid);
+/* device-resident, asynchronous: dQ[k] = device k's slice (rows lo_k .. hi_k-1, `layout` / `ld` as in the
+ * single-device call), d_bits_all[k] = device k's copy of the gathered bitmap.  Kernels run on every context's
+ * own stream, then ONE in-place ncclAllGather (communicators from ncclCommInitAll) completes every copy. */
+void aa_rx_cl_check_batch_multi_dev(struct aa_rx_cl_multi *m, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                    size_t n_q, const double *q_all_base, const void *const *dQ, int layout, size_t ld,
+                                    uint32_t *const *d_bits_all);
+void aa_rx_cl_check_edges_multi_dev(struct aa_rx_cl_multi *m, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                    size_t n_q, const double *q_all_base, const void *const *dQ0, const void *const *dQ1,
+                                    int layout, size_t ld, double seg_len, uint32_t *const *d_bits_all,
+                                    int32_t *const *d_first_slices);
+void aa_rx_cl_multi_sync(struct aa_rx_cl_multi *m);
+
+/* (2) one process per GPU (torchrun / MPI style launches): rank 0 makes an id, the caller distributes its
+ * TMK_SHARD_ID_BYTES bytes, every rank builds the communicator on its current device.  The call checks this
+ * rank's slice (dQ*_slice) into slot `rank` of d_bits_all and all-gathers in place, on `stream` (default) or,
+ * with tmk_shard_comm_overlap(c, 1), on the communicator's own high-priority stream so that the gather of one
+ * batch runs beside the kernels of the next (tmk_shard_comm_join makes a stream wait for what is in flight). */
+struct tmk_shard_comm;
+void tmk_shard_unique_id(void *id_bytes);
+struct tmk_shard_comm *tmk_shard_comm_create(int rank, int world, const void *id_bytes);
+void tmk_shard_comm_destroy(struct tmk_shard_comm *c);
+int tmk_shard_comm_rank(const struct tmk_shard_comm *c);
+int tmk_shard_comm_world(const struct tmk_shard_comm *c);
+void tmk_shard_comm_overlap(struct tmk_shard_comm *c, int enable);
+void tmk_shard_comm_join(struct tmk_shard_comm *c, void *stream);
+void aa_rx_cl_check_batch_shard_dev(struct aa_rx_cl *cl, struct tmk_shard_comm *c, size_t n_total, size_t n_sub,
+                                    const aa_rx_config_id *sub_ids, size_t n_q, const double *q_all_base,
+                                    const void *dQ_slice, int layout, size_t ld, uint32_t *d_bits_all, void *stream);
+void aa_rx_cl_check_edges_shard_dev(struct aa_rx_cl *cl, struct tmk_shard_comm *c, size_t n_total, size_t n_sub,
+                                    const aa_rx_config_id *sub_ids, size_t n_q, const double *q_all_base,
+                                    const void *dQ0_slice, const void *dQ1_slice, int layout, size_t ld, double seg_len,
+                                    uint32_t *d_bits_all, int32_t *d_first_slice, void *stream);
+
+/* Pinned host memory for the callers of the host-buffer entry points: pageable rows are staged by the driver
+ * at a fraction of the PCIe rate.  aa_rx_host_register returns 0 on success, -1 otherwise. */
+void *aa_rx_host_alloc(size_t bytes);
+void aa_rx_host_free(void *p);
+int aa_rx_host_register(void *p, size_t bytes);
+void aa_rx_host_unregister(void *p);
 
 /* OR of the colliding frame pairs over the last batch (the :track-collisions feed-back,
  * lisp/python/tmsmtpy.lisp:59; consumed by lisp/itmp-rec.lisp:230-247).  Enabled per handle. */

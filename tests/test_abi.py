@@ -59,6 +59,24 @@ def test_product_does_not_link_the_oracle(built):
                 assert "import oracle" not in txt and "from oracle" not in txt and "tmk_oracle" not in txt, f
 
 
+def test_shard_bounds_cover_the_batch_and_match_the_python_restatement(built):
+    """tmk_shard_bounds (multi.cu) = tmkit_b200/shard.py slice_bounds: contiguous, 1024-aligned, covering [0, n)"""
+    from tmkit_b200 import shard
+    for n in (0, 1, 1023, 1024, 1025, 100_000, (1 << 20) + 7, 1 << 24):
+        for world in (1, 2, 3, 4, 8):
+            per = A.lib().tmk_shard_per_rank(n, world)
+            assert per % A.SHARD_ALIGN == 0 and A.shard_words(n, world) * 32 == per
+            assert A.shard_words(n, world) == shard.words_per_rank(n, world)
+            want = shard.slice_bounds(n, world)
+            prev = 0
+            for r in range(world):
+                lo, hi = A.shard_bounds(n, world, r)
+                assert (lo, hi) == want[r]
+                assert lo == prev and lo <= hi <= n and (lo % A.SHARD_ALIGN == 0 or lo == n)
+                prev = hi
+            assert prev == n
+
+
 @pytest.fixture(scope="module")
 def sg(built):
     return A.SceneGraph.from_scene(S.baxter_sussman())

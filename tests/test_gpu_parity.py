@@ -446,11 +446,13 @@ def test_blocksworld_scaling_scenes(n_blocks):
     assert 0.02 < valid.mean() < 0.98
 
 
-@pytest.mark.parametrize("n_prims", [128, 512])
-def test_dual_arm_clutter_scene(n_prims):
+@pytest.mark.parametrize("n_prims,reject", [(128, True), (512, True), (512, False)])
+def test_dual_arm_clutter_scene(n_prims, reject):
     """14 varied joints, random primitives (boxes / cylinders / spheres); 512 = BASELINE configs[4]
-    (20 moving geometries, ~10K candidate pairs: the image is read through L1, not staged)."""
-    sc = S.clutter_scene(n_prims, seed=1)
+    (20 moving geometries, ~10K candidate pairs: the image is read through L1, not staged).  reject = obstacles
+    that touch the robot at q0 are redrawn; without it they stay and the start-state allowance
+    handles them (the round-1 scene, kept as a second case)."""
+    sc = S.clutter_scene(n_prims, seed=1, reject_at_q0=reject)
     q0 = S.q0_vector(sc)
     sg, cl, _ = _gpu_scene(sc, q0)
     orc = _oracle_scene(sc, q0)

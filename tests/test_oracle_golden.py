@@ -353,3 +353,30 @@ def test_bounding_sphere_culls_never_change_a_verdict(which):
         q[sub] = Q[c]
         p1, p2 = fresh_fast.check(fresh_fast.fk(q)[1]), fresh_brute.check(fresh_brute.fk(q)[1])
         assert p1[0] == p2[0] and p1[1] == p2[1] and np.array_equal(p1[2], p2[2])
+
+
+def test_clutter_scene_obstacles_do_not_touch_the_robot_at_q0(built):
+    """"rejecting any [obstacle] that intersect the robot at q0".  The generator's own
+    bounding test (tmkit_b200/scenes.py, device-free) is checked with the oracle's exact pair set at q0, and its FK
+    helper against the oracle's FK."""
+    from tmkit_b200 import scenes as S
+    for seed in (0, 1):
+        sc = S.clutter_scene(512, seed=seed)
+        orc = O.OracleScene(S.flatten(sc))
+        q0 = S.q0_vector(sc)
+        _, ab = orc.fk(q0)
+        tf = S.world_poses(sc, S.Q0)
+        for i, name in enumerate(orc.names):
+            r, v = tf[name]
+            sgn = 1.0 if np.dot(r, ab[i, :4]) >= 0 else -1.0
+            assert np.abs(sgn * r - ab[i, :4]).max() < 1e-12 and np.abs(v - ab[i, 4:]).max() < 1e-12
+        _, _, ps = orc.check(ab, want_set=True)
+        obs = np.asarray([n.startswith("obstacle_") for n in orc.names])
+        assert (ps[np.ix_(obs, ~obs)] != 0).sum() == 0 and (ps[np.ix_(~obs, obs)] != 0).sum() == 0
+        assert obs.sum() == 512
+    old = S.clutter_scene(512, seed=0, reject_at_q0=False)   # the round-1 scene keeps them
+    orc = O.OracleScene(S.flatten(old))
+    _, ab = orc.fk(S.q0_vector(old))
+    _, _, ps = orc.check(ab, want_set=True)
+    obs = np.asarray([n.startswith("obstacle_") for n in orc.names])
+    assert (ps[np.ix_(obs, ~obs)] != 0).sum() + (ps[np.ix_(~obs, obs)] != 0).sum() > 0

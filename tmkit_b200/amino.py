@@ -120,6 +120,38 @@ SIGNATURES = {
     "tmk_plan_motion_names": (_sz, [_vp, _sz]),
     "tmk_plan_motion_points": (_sz, [_vp, _sz]),
     "tmk_plan_motion_data": (_vp, [_vp, _sz]),
+    "tmk_shard_per_rank": (_sz, [_sz, _i]),
+    "tmk_shard_bounds": (None, [_sz, _i, _i, _vp, _vp]),
+    "tmk_shard_words": (_sz, [_sz, _i]),
+    "aa_rx_cl_multi_create": (_vp, [_vp, _i, _vp]),
+    "aa_rx_cl_multi_destroy": (None, [_vp]),
+    "aa_rx_cl_multi_device_count": (_i, [_vp]),
+    "aa_rx_cl_multi_device": (_i, [_vp, _i]),
+    "aa_rx_cl_multi_context": (_vp, [_vp, _i]),
+    "aa_rx_cl_multi_allow": (None, [_vp, _i, _i, _i]),
+    "aa_rx_cl_multi_allow_set": (None, [_vp, _vp]),
+    "aa_rx_cl_multi_allow_name": (None, [_vp, _cs, _cs, _i]),
+    "aa_rx_cl_multi_track_collisions": (None, [_vp, _i]),
+    "aa_rx_cl_multi_batch_collisions": (None, [_vp, _vp]),
+    "aa_rx_cl_check_batch_multi": (_sz, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "aa_rx_cl_check_batch_multi_f32": (_sz, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "aa_rx_cl_check_edges_multi": (_sz, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _d, _vp, _vp]),
+    "aa_rx_cl_check_batch_multi_dev": (None, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _i, _sz, _vp]),
+    "aa_rx_cl_check_edges_multi_dev": (None, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _i, _sz, _d, _vp, _vp]),
+    "aa_rx_cl_multi_sync": (None, [_vp]),
+    "tmk_shard_unique_id": (None, [_vp]),
+    "tmk_shard_comm_create": (_vp, [_i, _i, _vp]),
+    "tmk_shard_comm_destroy": (None, [_vp]),
+    "tmk_shard_comm_rank": (_i, [_vp]),
+    "tmk_shard_comm_world": (_i, [_vp]),
+    "tmk_shard_comm_overlap": (None, [_vp, _i]),
+    "tmk_shard_comm_join": (None, [_vp, _vp]),
+    "aa_rx_cl_check_batch_shard_dev": (None, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _i, _sz, _vp, _vp]),
+    "aa_rx_cl_check_edges_shard_dev": (None, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _i, _sz, _d, _vp, _vp, _vp]),
+    "aa_rx_host_alloc": (_vp, [_sz]),
+    "aa_rx_host_free": (None, [_vp]),
+    "aa_rx_host_register": (_i, [_vp, _sz]),
+    "aa_rx_host_unregister": (None, [_vp]),
     "aa_rx_cl_kernel_timing": (None, [_vp, _i]),
     "aa_rx_cl_kernel_time": (_sz, [_vp, _vp, _vp]),
     "tmk_fp32_peak_tflops": (_d, []),
@@ -137,6 +169,25 @@ class BatchStats(C.Structure):
 
 
 _lib = None
+SHARD_ALIGN = 1024
+SHARD_ID_BYTES = 128
+
+
+def _preload_nccl():
+    """libtmkcl.so needs libnccl.so.2 (the all-gather of the validity words).  A process that also imports torch
+    must end up with ONE NCCL: torch's bundled copy is loaded first when it exists, so that the soname is already
+    resolved (to the newer library) whichever of the two is imported first; otherwise the system one is used."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return cand
+    except Exception:
+        pass
+    return None
 
 
 def lib():
@@ -146,6 +197,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: build it (python -c 'import __graft_entry__ as g; g.build()'). "
                                "There is no CPU fallback.")
+        _preload_nccl()
         # RTLD_GLOBAL: dlopen'ed scene plugins resolve the aa_rx_* constructors against this library
         L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         for name, (res, args) in SIGNATURES.items():
@@ -477,6 +529,153 @@ class Collision:
             if self.h:
                 self.L.aa_rx_cl_destroy(self.h)
                 self.h = None
+        except Exception:
+            pass
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """tmk_shard_bounds: the slice [lo, hi) of rank `rank` (no device needed)."""
+    lo, hi = C.c_size_t(0), C.c_size_t(0)
+    lib().tmk_shard_bounds(n, world, rank, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def shard_words(n: int, world: int) -> int:
+    return lib().tmk_shard_words(n, world)
+
+
+class CollisionMulti:
+    """struct aa_rx_cl_multi: one handle over several GPUs of the box (one process)."""
+
+    def __init__(self, sg: SceneGraph, devices: Optional[Sequence[int]] = None):
+        self.L = lib()
+        self.sg = sg
+        if devices is None:
+            self.h = self.L.aa_rx_cl_multi_create(sg.h, 0, None)
+        else:
+            d = np.ascontiguousarray(devices, dtype=np.int32)
+            self.h = self.L.aa_rx_cl_multi_create(sg.h, len(d), _p(d))
+        self.n_dev = self.L.aa_rx_cl_multi_device_count(self.h)
+        self.devices = [self.L.aa_rx_cl_multi_device(self.h, k) for k in range(self.n_dev)]
+
+    def allow_set(self, s: CollisionSet):
+        self.L.aa_rx_cl_multi_allow_set(self.h, s.h)
+
+    def allow_name(self, a: str, b: str, allowed: int = 1):
+        self.L.aa_rx_cl_multi_allow_name(self.h, _b(a), _b(b), allowed)
+
+    def track_collisions(self, enable: bool = True):
+        self.L.aa_rx_cl_multi_track_collisions(self.h, int(enable))
+
+    def batch_collisions(self) -> CollisionSet:
+        s = CollisionSet(self.sg)
+        self.L.aa_rx_cl_multi_batch_collisions(self.h, s.h)
+        return s
+
+    def check_batch(self, sub_ids, q_base, Q):
+        sub = np.ascontiguousarray(sub_ids, dtype=np.int32)
+        qb = _f64(q_base)
+        Q = np.ascontiguousarray(Q)
+        n = Q.shape[0]
+        bits = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+        bits[-1] = 0xdeadbeef  # canary: nothing may be written past ceil(n / 32) words
+        if Q.dtype == np.float32:
+            bad = self.L.aa_rx_cl_check_batch_multi_f32(self.h, n, len(sub), _p(sub), len(qb), _p(qb), _p(Q), Q.shape[1], _p(bits))
+        else:
+            Q = _f64(Q)
+            bad = self.L.aa_rx_cl_check_batch_multi(self.h, n, len(sub), _p(sub), len(qb), _p(qb), _p(Q), Q.shape[1], _p(bits))
+        assert bits[-1] == 0xdeadbeef
+        valid = Collision.unpack_bits(bits, n)
+        assert int((~valid).sum()) == bad
+        return valid
+
+    def check_edges(self, sub_ids, q_base, Q0, Q1, seg_len: float, want_first: bool = True):
+        sub = np.ascontiguousarray(sub_ids, dtype=np.int32)
+        qb = _f64(q_base)
+        Q0, Q1 = _f64(Q0), _f64(Q1)
+        n = Q0.shape[0]
+        bits = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+        first = np.full(n + 1, -7, dtype=np.int32) if want_first else None
+        self.L.aa_rx_cl_check_edges_multi(self.h, n, len(sub), _p(sub), len(qb), _p(qb), _p(Q0), _p(Q1), Q0.shape[1],
+                                          float(seg_len), _p(bits), _p(first))
+        return Collision.unpack_bits(bits, n), (first[:n] if want_first else None)
+
+    def check_batch_dev(self, n, sub_ids, q_base, dQ: Sequence[int], layout: int, ld: int, d_bits_all: Sequence[int]):
+        """dQ[k] / d_bits_all[k]: raw device addresses on device k (slice rows / gathered bitmap)."""
+        sub = np.ascontiguousarray(sub_ids, dtype=np.int32)
+        qb = _f64(q_base)
+        a = (C.c_void_p * self.n_dev)(*dQ)
+        b = (C.c_void_p * self.n_dev)(*d_bits_all)
+        self.L.aa_rx_cl_check_batch_multi_dev(self.h, n, len(sub), _p(sub), len(qb), _p(qb), a, layout, ld, b)
+
+    def check_edges_dev(self, n, sub_ids, q_base, dQ0, dQ1, layout: int, ld: int, seg_len: float, d_bits_all,
+                        d_first=None):
+        sub = np.ascontiguousarray(sub_ids, dtype=np.int32)
+        qb = _f64(q_base)
+        a = (C.c_void_p * self.n_dev)(*dQ0)
+        a1 = (C.c_void_p * self.n_dev)(*dQ1)
+        b = (C.c_void_p * self.n_dev)(*d_bits_all)
+        f = (C.c_void_p * self.n_dev)(*d_first) if d_first is not None else None
+        self.L.aa_rx_cl_check_edges_multi_dev(self.h, n, len(sub), _p(sub), len(qb), _p(qb), a, a1, layout, ld,
+                                              float(seg_len), b, f)
+
+    def sync(self):
+        self.L.aa_rx_cl_multi_sync(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.aa_rx_cl_multi_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class ShardComm:
+    """struct tmk_shard_comm: one process per GPU; the 128-byte id is made by rank 0 (ShardComm.unique_id) and
+    distributed by the caller (torch.distributed broadcast, MPI, a file ...)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(SHARD_ID_BYTES)
+        lib().tmk_shard_unique_id(buf)
+        return buf.raw
+
+    def __init__(self, rank: int, world: int, id_bytes: bytes):
+        self.L = lib()
+        assert len(id_bytes) == SHARD_ID_BYTES
+        self._id = C.create_string_buffer(id_bytes, SHARD_ID_BYTES)
+        self.rank, self.world = rank, world
+        self.h = self.L.tmk_shard_comm_create(rank, world, self._id)
+
+    def overlap(self, enable: bool = True):
+        self.L.tmk_shard_comm_overlap(self.h, int(enable))
+
+    def join(self, stream: int = 0):
+        self.L.tmk_shard_comm_join(self.h, stream or None)
+
+    def check_batch_dev(self, cl: Collision, n_total, sub_ids, q_base, dQ_slice: int, layout: int, ld: int,
+                        d_bits_all: int, stream: int = 0):
+        sub = np.ascontiguousarray(sub_ids, dtype=np.int32)
+        qb = _f64(q_base)
+        self.L.aa_rx_cl_check_batch_shard_dev(cl.h, self.h, n_total, len(sub), _p(sub), len(qb), _p(qb), dQ_slice,
+                                              layout, ld, d_bits_all, stream or None)
+
+    def check_edges_dev(self, cl: Collision, n_total, sub_ids, q_base, dQ0: int, dQ1: int, layout: int, ld: int,
+                        seg_len: float, d_bits_all: int, d_first: int = 0, stream: int = 0):
+        sub = np.ascontiguousarray(sub_ids, dtype=np.int32)
+        qb = _f64(q_base)
+        self.L.aa_rx_cl_check_edges_shard_dev(cl.h, self.h, n_total, len(sub), _p(sub), len(qb), _p(qb), dQ0, dQ1,
+                                              layout, ld, float(seg_len), d_bits_all, d_first or None, stream or None)
+
+    def destroy(self):
+        if self.h:
+            self.L.tmk_shard_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
         except Exception:
             pass
 

@@ -170,20 +170,39 @@ struct SgDev {
     DBuf ik_in, ik_out;        /* tmk_dev_ik: one upload, one launch, one download per goal */
     size_t n_f = 0;
 };
+/* one mirror per CUDA device that has touched the scene graph (multi-GPU: a replica per device) */
+#define TMK_MAX_DEV 16
+struct SgDevSet { SgDev *d[TMK_MAX_DEV] = {nullptr}; };
 
 extern "C" void tmk_dev_sg_release(void *dev) {
-    SgDev *d = (SgDev *)dev;
-    if (!d) return;
-    cudaDeviceSynchronize();
-    d->frames.release(); d->q.release(); d->rel.release(); d->ab.release();
-    d->b_frames.release(); d->b_q.release(); d->b_out.release();
-    d->ik_in.release(); d->ik_out.release();
-    delete d;
+    SgDevSet *set = (SgDevSet *)dev;
+    if (!set) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int k = 0; k < TMK_MAX_DEV; k++) {
+        SgDev *d = set->d[k];
+        if (!d) continue;
+        cudaSetDevice(k); /* the buffers go back to the pool under their own device */
+        cudaDeviceSynchronize();
+        d->frames.release(); d->q.release(); d->rel.release(); d->ab.release();
+        d->b_frames.release(); d->b_q.release(); d->b_out.release();
+        d->ik_in.release(); d->ik_out.release();
+        delete d;
+    }
+    cudaSetDevice(cur);
+    delete set;
 }
 
 static SgDev *sg_dev(const struct aa_rx_sg *sg) {
     struct aa_rx_sg *m = (struct aa_rx_sg *)sg; /* cache slot is logically mutable */
-    if (m->dev) return (SgDev *)m->dev;
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    if (cur < 0 || cur >= TMK_MAX_DEV) tmk_die("device ordinal %d outside 0..%d", cur, TMK_MAX_DEV - 1);
+    static std::mutex mu; /* the per-device contexts of a multi-GPU handle may be built from several threads */
+    std::lock_guard<std::mutex> lock(mu);
+    if (!m->dev) m->dev = new SgDevSet();
+    SgDevSet *set = (SgDevSet *)m->dev;
+    if (set->d[cur]) return set->d[cur];
     SgDev *d = new SgDev();
     std::vector<DFrame> fr(sg->n_f);
     for (size_t i = 0; i < sg->n_f; i++) {
@@ -201,7 +220,7 @@ static SgDev *sg_dev(const struct aa_rx_sg *sg) {
     d->rel.need(sizeof(double) * 7 * (sg->n_f + 1));
     d->ab.need(sizeof(double) * 7 * (sg->n_f + 1));
     CK(cudaDeviceSynchronize());
-    m->dev = d;
+    set->d[cur] = d;
     return d;
 }
 
@@ -371,6 +390,7 @@ struct ImageDev {
 
 struct aa_rx_cl {
     const struct aa_rx_sg *sg;
+    int dev; /* the CUDA device the context lives on: every call on it must be made with that device current */
     size_t n_f, n_q, n_g, wpr;
     uint32_t *allowed; /* own copy */
     uint64_t allow_serial;
@@ -517,6 +537,7 @@ extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
     HostSpan hs("cl_create");
     struct aa_rx_cl *cl = new aa_rx_cl();
     cl->sg = sg;
+    CK(cudaGetDevice(&cl->dev));
     cl->n_f = sg->n_f; cl->n_q = sg->n_q; cl->n_g = sg->n_g; cl->wpr = sg->wpr;
     cl->allowed = (uint32_t *)malloc(sizeof(uint32_t) * (cl->n_f * cl->wpr + 1));
     memcpy(cl->allowed, sg->allowed, sizeof(uint32_t) * cl->n_f * cl->wpr);
@@ -542,6 +563,9 @@ extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
 extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     if (!cl) return;
     HostSpan hs("cl_destroy");
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev != cl->dev) cudaSetDevice(cl->dev); /* buffers and streams go back to the pools of their device */
     cudaDeviceSynchronize(); /* the scratch buffers go back to the pool: nothing may still use them */
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
                     &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_conv, &cl->d_tri, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
@@ -560,6 +584,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
         g_stream_pool.give(ss);
     }
     free(cl->allowed);
+    if (cur_dev != cl->dev) cudaSetDevice(cur_dev);
     delete cl;
     hs.mark("all");
 }
@@ -652,6 +677,11 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
                          const double *q_base) {
     const struct aa_rx_sg *sg = cl->sg;
     ImageDev &im = cl->img;
+    {
+        int cur = -1;
+        CK(cudaGetDevice(&cur));
+        if (cur != cl->dev) tmk_die("batch: the collision context lives on device %d but device %d is current", cl->dev, cur);
+    }
     if (n_q != cl->n_q) tmk_die("batch: n_q = %zu, scene graph has %zu", n_q, cl->n_q);
     if (n_sub < 1 || n_sub > TMK_MAXSUB) tmk_die("batch: n_sub = %zu outside 1..%d", n_sub, TMK_MAXSUB);
     bool same = im.valid && im.allow_serial == cl->allow_serial && im.sub.size() == n_sub &&
@@ -1246,7 +1276,7 @@ static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, co
         int32_t *nd = (int32_t *)cl->d_nd.p, *first = (int32_t *)cl->d_efirst.p;
         cudaEvent_t *ev = timing_begin(cl, s);
         k_edges_prep<<<(ne + 255) / 256, 256, 0, s>>>(dQ0, dQ1, layout, ld, im.f.n_sub, ne, seg_len, nd, first,
-                                                      im.f.static_hit);
+                                                      im.f.static_hit, 1 << (n_levels - 1), cnt + 1);
         CK(cudaGetLastError());
         SrcEdgeLevel src;
         src.p0 = dQ0; src.p1 = dQ1; src.layout = layout; src.ld = ld; src.nd = nd; src.n_edge = ne;
@@ -1372,11 +1402,14 @@ static size_t count_invalid(const uint32_t *bits, size_t n) {
     return n - valid;
 }
 
-static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
-                               size_t n_q, const double *q_base, const void *Q, int layout, size_t ldQ,
-                               uint32_t *valid_bits) {
+/* The host-buffer call in two halves, so that a multi-GPU caller (multi.cu) can enqueue the slices of all devices
+ * before it waits for any of them: begin() enqueues copies, kernels and the read-back of the validity words,
+ * end() synchronises, collects the counters and counts the invalid units. */
+static void batch_host_begin(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                             size_t n_q, const double *q_base, const void *Q, int layout, size_t ldQ,
+                             uint32_t *valid_bits) {
     if (ldQ < n_sub) tmk_die("batch: ldQ < n_sub");
-    HostSpan hs("check_batch_host");
+    HostSpan hs("batch_host_begin");
     ensure_image(cl, n_sub, sub_ids, n_q, q_base);
     stats_begin(cl);
     size_t esz = layout == TMK_Q_ROWS_F64 ? 8 : 4;
@@ -1408,12 +1441,23 @@ static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, 
     }
     if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
     hs.mark("enqueued");
-    stats_end(cl, n_cfg, cl->stream);
+}
+
+static size_t batch_host_end(struct aa_rx_cl *cl, size_t n_units, const uint32_t *valid_bits) {
+    HostSpan hs("batch_host_end");
+    stats_end(cl, n_units, cl->stream);
     hs.mark("synchronised");
-    size_t bad = count_invalid(valid_bits, n_cfg);
+    size_t bad = count_invalid(valid_bits, n_units);
     cl->stats.n_invalid = bad;
     hs.mark("counted");
     return bad;
+}
+
+static size_t check_batch_host(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                               size_t n_q, const double *q_base, const void *Q, int layout, size_t ldQ,
+                               uint32_t *valid_bits) {
+    batch_host_begin(cl, n_cfg, n_sub, sub_ids, n_q, q_base, Q, layout, ldQ, valid_bits);
+    return batch_host_end(cl, n_cfg, valid_bits);
 }
 
 extern "C" size_t aa_rx_cl_check_batch(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
@@ -1427,9 +1471,9 @@ extern "C" size_t aa_rx_cl_check_batch_f32(struct aa_rx_cl *cl, size_t n_cfg, si
     return check_batch_host(cl, n_cfg, n_sub, sub_ids, n_q, q_all_base, Q_sub, TMK_Q_ROWS_F32, ldQ, valid_bits);
 }
 
-extern "C" size_t aa_rx_cl_check_edges(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
-                                       size_t n_q, const double *q_all_base, const double *Q0, const double *Q1,
-                                       size_t ldQ, double seg_len, uint32_t *valid_bits, int32_t *first_invalid) {
+static void edges_host_begin(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
+                             size_t n_q, const double *q_all_base, const double *Q0, const double *Q1, size_t ldQ,
+                             double seg_len, uint32_t *valid_bits, int32_t *first_invalid) {
     if (ldQ < n_sub) tmk_die("edges: ldQ < n_sub");
     ensure_image(cl, n_sub, sub_ids, n_q, q_all_base);
     stats_begin(cl);
@@ -1443,7 +1487,8 @@ extern "C" size_t aa_rx_cl_check_edges(struct aa_rx_cl *cl, size_t n_edge, size_
         CK(cudaMemcpyAsync(cl->d_q1.p, Q1, n_edge * ldQ * 8, cudaMemcpyHostToDevice, cl->stream));
     }
     /* small batches (a planner's frontier): the longest edge bounds the bisection depth, and the dead levels
-     * are launches the host can see and skip.  +2 segments of slack: the device count is authoritative. */
+     * are launches the host can see and skip.  +2 segments of slack: the device count is authoritative (an edge
+     * that needs more levels than were launched raises the overflow flag, see k_edges_prep). */
     int n_levels = TMK_EDGE_LEVELS;
     if (n_edge && n_edge <= 4096 && seg_len > 0) {
         double s2max = 0;
@@ -1467,11 +1512,32 @@ extern "C" size_t aa_rx_cl_check_edges(struct aa_rx_cl *cl, size_t n_edge, size_
     if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
     if (first_invalid && n_edge)
         CK(cudaMemcpyAsync(first_invalid, cl->d_first.p, sizeof(int32_t) * n_edge, cudaMemcpyDeviceToHost, cl->stream));
-    stats_end(cl, n_edge, cl->stream);
-    size_t bad = count_invalid(valid_bits, n_edge);
-    cl->stats.n_invalid = bad;
-    return bad;
 }
+
+extern "C" size_t aa_rx_cl_check_edges(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                       size_t n_q, const double *q_all_base, const double *Q0, const double *Q1,
+                                       size_t ldQ, double seg_len, uint32_t *valid_bits, int32_t *first_invalid) {
+    edges_host_begin(cl, n_edge, n_sub, sub_ids, n_q, q_all_base, Q0, Q1, ldQ, seg_len, valid_bits, first_invalid);
+    return batch_host_end(cl, n_edge, valid_bits);
+}
+
+/* the two halves for multi.cu (declared in tmk_internal.h) */
+extern "C" void tmk_cl_batch_host_begin(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                        size_t n_q, const double *q_base, const void *Q, int layout, size_t ldQ,
+                                        uint32_t *valid_bits) {
+    batch_host_begin(cl, n_cfg, n_sub, sub_ids, n_q, q_base, Q, layout, ldQ, valid_bits);
+}
+extern "C" void tmk_cl_edges_host_begin(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                        size_t n_q, const double *q_base, const double *Q0, const double *Q1, size_t ldQ,
+                                        double seg_len, uint32_t *valid_bits, int32_t *first_invalid) {
+    edges_host_begin(cl, n_edge, n_sub, sub_ids, n_q, q_base, Q0, Q1, ldQ, seg_len, valid_bits, first_invalid);
+}
+extern "C" size_t tmk_cl_host_end(struct aa_rx_cl *cl, size_t n_units, const uint32_t *valid_bits) {
+    return batch_host_end(cl, n_units, valid_bits);
+}
+extern "C" int tmk_cl_device(const struct aa_rx_cl *cl) { return cl->dev; }
+extern "C" void *tmk_cl_stream(const struct aa_rx_cl *cl) { return (void *)cl->stream; }
+extern "C" const struct aa_rx_sg *tmk_cl_sg(const struct aa_rx_cl *cl) { return cl->sg; }
 
 extern "C" void aa_rx_cl_check_batch_dev(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
                                          size_t n_q, const double *q_all_base, const void *dQ, int layout, size_t ld,

@@ -327,6 +327,7 @@ __global__ void k_fk_batch(const FFrame *fr_g, int n_f, const double *Q, size_t 
     }
 }
 
+#define TMK_ND_MAX (1 << 24) /* segments per edge are clamped here: 1.7e7 states on one edge is misuse, not a workload */
 /* number of segments: ceil(|b-a|_2 / seg_len), at least 1 - evaluated in double with
  * round-to-nearest ops in index order so that it matches the host restatement bit for bit */
 __device__ __forceinline__ int segment_count(const double *a, const double *b, int n, double seg_len) {
@@ -335,8 +336,10 @@ __device__ __forceinline__ int segment_count(const double *a, const double *b, i
         double d = __dsub_rn(b[k], a[k]);
         s = __dadd_rn(s, __dmul_rn(d, d));
     }
-    int nd = (int)ceil(__ddiv_rn(__dsqrt_rn(s), seg_len));
-    return nd < 1 ? 1 : nd;
+    const double r = ceil(__ddiv_rn(__dsqrt_rn(s), seg_len));
+    if (!(r >= 1.0)) return 1;                      /* zero-length edge (or NaN end points: one state, Q1) */
+    if (r > (double)TMK_ND_MAX) return TMK_ND_MAX;  /* the cast below is only defined inside int's range */
+    return (int)r;
 }
 
 /* ------------------------------------------------------------------ K4: swept edges, one warp per edge */

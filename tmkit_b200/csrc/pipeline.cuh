@@ -163,7 +163,9 @@ struct SinkBits {
     __device__ __forceinline__ void emit(const SrcConfigs::State &st, size_t g, bool hit, int lane) const {
         (void)g;
         const unsigned valid = __ballot_sync(0xffffffffu, !hit);
-        if (lane == 0) bits[st.s >> 5] = valid;
+        /* lane 0 holds the warp's first state: if it lies past the batch the whole warp does, and its word is
+         * past ceil(n / 32) - the caller's bitmap has no padding (slices of a sharded bitmap touch each other) */
+        if (lane == 0 && st.live) bits[st.s >> 5] = valid;
     }
     __device__ __forceinline__ void mark_hit(const SrcConfigs::State &st) const {
         atomicAnd(&bits[st.s >> 5], ~(1u << (st.s & 31)));
@@ -854,8 +856,12 @@ __global__ void __launch_bounds__(128) k_overflow_all(Image<double> im, Src src,
 
 /* ------------------------------------------------------------------ swept-edge bookkeeping kernels */
 /* segments per edge (double, bit-identical to the host restatement) and first[] reset */
+/* An edge with more segments than the launched bisection levels cover (positions 0 .. max_nd - 1) cannot be
+ * decided level by level: it raises the overflow flag and k_edges_overflow_all walks every edge's states in
+ * OMPL order instead (slow, exact, and only for a seg_len far below the reference's 1 % resolution). */
 __global__ void k_edges_prep(const void *p0, const void *p1, int layout, size_t ld, int n_sub, uint32_t n_edge,
-                             double seg_len, int32_t *nd, int32_t *first, int static_hit) {
+                             double seg_len, int32_t *nd, int32_t *first, int static_hit, int max_nd,
+                             uint32_t *overflow) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edge) return;
     double a[TMK_MAXSUB], b[TMK_MAXSUB];
@@ -863,8 +869,10 @@ __global__ void k_edges_prep(const void *p0, const void *p1, int layout, size_t 
         a[k] = load_q<double>(p0, layout, ld, e, k);
         b[k] = load_q<double>(p1, layout, ld, e, k);
     }
-    nd[e] = segment_count(a, b, n_sub, seg_len);
+    const int n = segment_count(a, b, n_sub, seg_len);
+    nd[e] = n;
     first[e] = static_hit ? 0 : TMK_FIRST_NONE;
+    if (n > max_nd) *overflow = 1u;
 }
 
 /* survivors of level L that have states at level L+1 (nd > 2^L) */

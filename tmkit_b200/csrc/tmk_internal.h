@@ -118,6 +118,17 @@ int tmk_dev_ik(const struct aa_rx_sg *sg, size_t n_fr, const aa_rx_frame_id *fra
                const double *goal, size_t n_seed, double *Q, double *err, int max_iter, int enough, int min_iter,
                double tol);
 
+/* cl.cu: the host-buffer calls in two halves (enqueue / wait), for the multi-GPU wrappers in multi.cu */
+void tmk_cl_batch_host_begin(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids, size_t n_q,
+                             const double *q_base, const void *Q, int layout, size_t ldQ, uint32_t *valid_bits);
+void tmk_cl_edges_host_begin(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, const aa_rx_config_id *sub_ids, size_t n_q,
+                             const double *q_base, const double *Q0, const double *Q1, size_t ldQ, double seg_len,
+                             uint32_t *valid_bits, int32_t *first_invalid);
+size_t tmk_cl_host_end(struct aa_rx_cl *cl, size_t n_units, const uint32_t *valid_bits);
+int tmk_cl_device(const struct aa_rx_cl *cl);
+void *tmk_cl_stream(const struct aa_rx_cl *cl);
+const struct aa_rx_sg *tmk_cl_sg(const struct aa_rx_cl *cl);
+
 #ifdef __cplusplus
 }
 #endif

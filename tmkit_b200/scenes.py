@@ -1,7 +1,8 @@
 """Neutral scene descriptions used on both sides of the parity check.
 
 A scene here is plain data (frames, geometry, allowed pairs) - no arithmetic beyond
-constant folding.  The same description is pushed (a) through the product's
+constant folding (one exception: ``clutter_scene`` rejects random obstacles that touch the robot at the start
+configuration with a conservative bounding test of its own, ``world_poses``).  The same description is pushed (a) through the product's
 scene-ingest C ABI (``aa_rx_sg_add_frame_*`` / ``aa_rx_geom_*``, see
 ``include/tmkit_b200/amino_rx.h``) and (b) into flat numpy arrays for the CPU oracle.
 
@@ -401,23 +402,117 @@ def _rand_quat(rng) -> Tuple[float, float, float, float]:
     return tuple(float(x) for x in q)
 
 
-def clutter_scene(n_prims: int = 512, seed: int = 0, mesh_res: int = 6) -> Scene:
-    """C5: Baxter + n random primitives: 50 % boxes (extents U(0.02,0.3)^3), 30 %
+def _q_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _q_rot(q, v):
+    u = np.asarray(q[:3], dtype=np.float64)
+    v = np.asarray(v, dtype=np.float64)
+    t = 2.0 * np.cross(u, v)
+    return v + q[3] * t + np.cross(u, t)
+
+
+def world_poses(sc: Scene, q: Dict[str, float]) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
+    """World pose (quaternion xyzw, translation) of every frame at the configuration ``q`` (variables not
+    listed are 0).  Scene-authoring aid only (the rejection test of ``clutter_scene``): the product's FK is
+    aa_rx_sg_tf, the oracle's is oracle/tmk_oracle.c."""
+    out: Dict[str, Tuple[np.ndarray, np.ndarray]] = {"": (np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3))}
+    pending = list(sc.frames)
+    while pending:
+        rest = []
+        for f in pending:
+            if f.parent not in out:
+                rest.append(f)
+                continue
+            r, v = np.asarray(f.quat, dtype=np.float64), np.asarray(f.xyz, dtype=np.float64)
+            if f.type == REVOLUTE:
+                ang = q.get(f.config, 0.0) + f.offset
+                ax = np.asarray(f.axis, dtype=np.float64)
+                r = _q_mul(r, np.concatenate([ax * math.sin(ang / 2), [math.cos(ang / 2)]]))
+            elif f.type == PRISMATIC:
+                v = v + _q_rot(r, np.asarray(f.axis, dtype=np.float64) * (q.get(f.config, 0.0) + f.offset))
+            pr, pv = out[f.parent]
+            out[f.name] = (_q_mul(pr, r), _q_rot(pr, v) + pv)
+        if len(rest) == len(pending):
+            raise ValueError("cycle or unknown parent in scene graph")
+        pending = rest
+    return out
+
+
+def _bounds_at(sc: Scene, q: Dict[str, float]):
+    """Conservative world-frame bounds of every geometry at q: spheres, capsules (cylinders) and oriented
+    boxes (boxes; meshes by the box of their vertices)."""
+    tf = world_poses(sc, q)
+    out = []
+    for f in sc.frames:
+        r, v = tf[f.name]
+        for g in f.geoms:
+            if g.shape == SPHERE:
+                out.append(("sphere", v, float(g.dims[0])))
+            elif g.shape == CYLINDER:  # base at the frame origin, axis +z
+                out.append(("capsule", v, v + _q_rot(r, (0.0, 0.0, float(g.dims[0]))), float(g.dims[1])))
+            elif g.shape == BOX:
+                out.append(("obb", r, v, 0.5 * np.asarray(g.dims, dtype=np.float64)))
+            else:
+                vv = np.asarray(g.verts, dtype=np.float64)
+                lo, hi = vv.min(axis=0), vv.max(axis=0)
+                out.append(("obb", r, v + _q_rot(r, 0.5 * (lo + hi)), 0.5 * (hi - lo)))
+    return out
+
+
+def _ball_touches(bounds, c, rho: float) -> bool:
+    c = np.asarray(c, dtype=np.float64)
+    for b in bounds:
+        if b[0] == "sphere":
+            d = np.linalg.norm(c - b[1]) - b[2]
+        elif b[0] == "capsule":
+            p0, p1 = b[1], b[2]
+            e = p1 - p0
+            t = min(1.0, max(0.0, float(np.dot(c - p0, e) / max(np.dot(e, e), 1e-30))))
+            d = np.linalg.norm(c - (p0 + t * e)) - b[3]
+        else:
+            r, centre, half = b[1], b[2], b[3]
+            local = _q_rot(np.array([-r[0], -r[1], -r[2], r[3]]), c - centre)
+            d = np.linalg.norm(np.maximum(np.abs(local) - half, 0.0))
+        if d <= rho:
+            return True
+    return False
+
+
+def clutter_scene(n_prims: int = 512, seed: int = 0, mesh_res: int = 6, reject_at_q0: bool = True) -> Scene:
+    """C5 (SURVEY.md 8d): Baxter + n random primitives: 50 % boxes (extents U(0.02,0.3)^3), 30 %
     cylinders (r U(0.01,0.1), h U(0.05,0.4)), 20 % spheres (r U(0.02,0.15)); centres
-    U([-1.5,1.5]^2 x [-0.5,1.5]); uniform orientations.  Obstacles intersecting the
-    robot at q0 are handled by the start-state allowance, as the reference does."""
+    U([-1.5,1.5]^2 x [-0.5,1.5]); uniform orientations; candidates that intersect the robot at the start
+    configuration ``Q0`` are rejected and redrawn.  The rejection test is conservative and device-free: the
+    candidate's bounding ball against capsule / oriented-box / sphere bounds of the robot geometry at Q0 (it
+    rejects every intersecting candidate and a few near misses).  ``reject_at_q0=False`` gives the round-1 scene,
+    where such obstacles stay and are handled by the start-state allowance (kept as a second test: 98 % of its
+    configurations are invalid)."""
     rng = np.random.default_rng(seed)
     sc = baxter_fixture(mesh_res)
-    for i in range(n_prims):
+    bounds = _bounds_at(sc, Q0) if reject_at_q0 else None
+    i = 0
+    while i < n_prims:
         u = rng.random()
         c = (float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-0.5, 1.5)))
         if u < 0.5:
             g = Geom(BOX, tuple(float(x) for x in rng.uniform(0.02, 0.3, size=3)))
+            centre_local, rho = (0.0, 0.0, 0.0), 0.5 * float(np.linalg.norm(g.dims))
         elif u < 0.8:
             g = Geom(CYLINDER, (float(rng.uniform(0.05, 0.4)), float(rng.uniform(0.01, 0.1)), 0.0))
+            centre_local, rho = (0.0, 0.0, 0.5 * g.dims[0]), math.hypot(0.5 * g.dims[0], g.dims[1])
         else:
             g = Geom(SPHERE, (float(rng.uniform(0.02, 0.15)), 0.0, 0.0))
-        sc.add(Frame(f"obstacle_{i}", "", FIXED, _rand_quat(rng), c, geoms=[g]))
+            centre_local, rho = (0.0, 0.0, 0.0), g.dims[0]
+        quat = _rand_quat(rng)
+        if bounds is not None and _ball_touches(bounds, np.asarray(c) + _q_rot(np.asarray(quat), centre_local), rho + 1e-6):
+            continue
+        sc.add(Frame(f"obstacle_{i}", "", FIXED, quat, c, geoms=[g]))
+        i += 1
     sc.allowed = list(ALLOWED_BAXTER)
     return sc
 
