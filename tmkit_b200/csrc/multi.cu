@@ -72,8 +72,12 @@ struct tmk_shard_comm {
     int rank, world, dev;
     int overlap;              /* 1: the all-gather runs on `cs`, beside the kernels of the next call */
     cudaStream_t cs;          /* high priority: tiny, and every peer waits for it */
-    cudaEvent_t ev_done, ev_gathered;
-    int pending;
+    cudaEvent_t ev_done;
+    /* gathers in flight on `cs` (overlap mode), by the bitmap they complete: a later call that writes the same
+     * bitmap first makes its stream wait for that gather - and only for that one, so that a caller alternating
+     * between two bitmaps overlaps the gather of batch k with the kernels of batch k+1 */
+    struct { const void *buf; cudaEvent_t ev; int pending; } fly[2];
+    int next_fly;
 };
 
 extern "C" void tmk_shard_unique_id(void *id128) {
@@ -86,7 +90,7 @@ extern "C" void tmk_shard_unique_id(void *id128) {
 extern "C" struct tmk_shard_comm *tmk_shard_comm_create(int rank, int world, const void *id128) {
     if (world < 1 || rank < 0 || rank >= world) tmk_die("tmk_shard_comm_create: rank %d of %d", rank, world);
     struct tmk_shard_comm *c = new tmk_shard_comm();
-    c->rank = rank; c->world = world; c->overlap = 0; c->pending = 0;
+    c->rank = rank; c->world = world; c->overlap = 0; c->next_fly = 0;
     CK(cudaGetDevice(&c->dev));
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
@@ -95,7 +99,10 @@ extern "C" struct tmk_shard_comm *tmk_shard_comm_create(int rank, int world, con
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&c->cs, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&c->fly[k].ev, cudaEventDisableTiming));
+        c->fly[k].buf = nullptr; c->fly[k].pending = 0;
+    }
     return c;
 }
 
@@ -104,7 +111,7 @@ extern "C" void tmk_shard_comm_destroy(struct tmk_shard_comm *c) {
     cudaStreamSynchronize(c->cs);
     ncclCommDestroy(c->comm);
     cudaEventDestroy(c->ev_done);
-    cudaEventDestroy(c->ev_gathered);
+    for (int k = 0; k < 2; k++) cudaEventDestroy(c->fly[k].ev);
     cudaStreamDestroy(c->cs);
     delete c;
 }
@@ -114,8 +121,20 @@ extern "C" void tmk_shard_comm_overlap(struct tmk_shard_comm *c, int enable) { c
 
 /* `stream` waits for the gathers still in flight on the communicator's own stream (overlap mode) */
 extern "C" void tmk_shard_comm_join(struct tmk_shard_comm *c, void *stream) {
-    if (c->pending) CK(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_gathered, 0));
-    c->pending = 0;
+    for (int k = 0; k < 2; k++)
+        if (c->fly[k].pending) {
+            CK(cudaStreamWaitEvent((cudaStream_t)stream, c->fly[k].ev, 0));
+            c->fly[k].pending = 0;
+        }
+}
+
+/* before `s` writes into d_bits_all again: wait for the gather in flight that still reads / completes it */
+static void wait_bitmap_free(struct tmk_shard_comm *c, const void *d_bits_all, cudaStream_t s) {
+    for (int k = 0; k < 2; k++)
+        if (c->fly[k].pending && c->fly[k].buf == d_bits_all) {
+            CK(cudaStreamWaitEvent(s, c->fly[k].ev, 0));
+            c->fly[k].pending = 0;
+        }
 }
 
 /* in place: this rank's words already sit in slot `rank` of d_bits_all */
@@ -128,8 +147,12 @@ static void gather_words(struct tmk_shard_comm *c, uint32_t *d_bits_all, size_t 
     CK(cudaEventRecord(c->ev_done, s));
     CK(cudaStreamWaitEvent(c->cs, c->ev_done, 0));
     NK(ncclAllGather(d_bits_all + (size_t)c->rank * wpr, d_bits_all, wpr, ncclUint32, c->comm, c->cs));
-    CK(cudaEventRecord(c->ev_gathered, c->cs));
-    c->pending = 1;
+    const int k = c->next_fly;
+    c->next_fly ^= 1;
+    if (c->fly[k].pending) CK(cudaStreamWaitEvent(s, c->fly[k].ev, 0)); /* a third bitmap: the oldest gather is joined */
+    CK(cudaEventRecord(c->fly[k].ev, c->cs));
+    c->fly[k].buf = d_bits_all;
+    c->fly[k].pending = 1;
 }
 
 extern "C" void aa_rx_cl_check_batch_shard_dev(struct aa_rx_cl *cl, struct tmk_shard_comm *c, size_t n_total, size_t n_sub,
@@ -141,6 +164,7 @@ extern "C" void aa_rx_cl_check_batch_shard_dev(struct aa_rx_cl *cl, struct tmk_s
     const size_t wpr = tmk_shard_words(n_total, c->world);
     cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)tmk_cl_stream(cl);
     uint32_t *slot = d_bits_all + (size_t)c->rank * wpr;
+    wait_bitmap_free(c, d_bits_all, s);
     zero_slot_tail(slot, hi - lo, wpr, s);
     aa_rx_cl_check_batch_dev(cl, hi - lo, n_sub, sub_ids, n_q, q_all_base, dQ_slice, layout, ld, slot, s);
     gather_words(c, d_bits_all, wpr, s);
@@ -155,6 +179,7 @@ extern "C" void aa_rx_cl_check_edges_shard_dev(struct aa_rx_cl *cl, struct tmk_s
     const size_t wpr = tmk_shard_words(n_total, c->world);
     cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)tmk_cl_stream(cl);
     uint32_t *slot = d_bits_all + (size_t)c->rank * wpr;
+    wait_bitmap_free(c, d_bits_all, s);
     zero_slot_tail(slot, hi - lo, wpr, s);
     aa_rx_cl_check_edges_dev(cl, hi - lo, n_sub, sub_ids, n_q, q_all_base, dQ0_slice, dQ1_slice, layout, ld, seg_len, slot,
                              d_first_slice, s);

@@ -419,7 +419,7 @@ def _q_rot(q, v):
 def world_poses(sc: Scene, q: Dict[str, float]) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
     """World pose (quaternion xyzw, translation) of every frame at the configuration ``q`` (variables not
     listed are 0).  Scene-authoring aid only (the rejection test of ``clutter_scene``): the product's FK is
-    aa_rx_sg_tf, the oracle's is oracle/tmk_oracle.c."""
+    aa_rx_sg_tf; the CPU checker has its own."""
     out: Dict[str, Tuple[np.ndarray, np.ndarray]] = {"": (np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3))}
     pending = list(sc.frames)
     while pending:
