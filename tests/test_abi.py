@@ -41,6 +41,23 @@ def test_library_exports_every_declared_symbol(built):
     assert b"sm_100a" in L.tmk_version()
 
 
+def test_library_exports_the_reference_plan_file_abi(built):
+    """every function include/tmkit_b200/tmplan.h declares (the names of /root/reference/include/tmsmt/tmplan.h)"""
+    src = open(os.path.join(ROOT, "include", "tmkit_b200", "tmplan.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decl = sorted(set(re.findall(r"\b(tmplan_[a-z0-9_]+)\s*\(", src)))
+    assert len(decl) >= 29, decl
+    out = subprocess.run(["nm", "-D", "--defined-only", A.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert not [n for n in decl if n not in exported]
+    # the reference header's names, as listed in its public API (tmplan.h:34-247), all appear
+    for n in ("tmplan_parse_filename", "tmplan_parse_file", "tmplan_map_ops", "tmplan_op_type", "tmplan_op_action_get",
+              "tmplan_op_motion_plan_path", "tmplan_op_motion_plan_config_count", "tmplan_op_motion_plan_path_size",
+              "tmplan_op_motion_plan_vars", "tmplan_op_motion_plan_map_var", "tmplan_op_reparent_get_frame",
+              "tmplan_op_reparent_get_new_parent", "tmplan_write", "tmplan_create", "tmplan_op_count"):
+        assert n in decl, n
+
+
 def test_library_is_sm100a_only(built):
     out = subprocess.run(["cuobjdump", "--list-elf", A.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))

@@ -145,6 +145,95 @@ def test_collision_feedback(built):
     pytest.fail("every sampled goal was directly reachable")
 
 
+def test_collision_feedback_reports_the_first_invalid_state_of_an_edge(built):
+    """ADVICE r1 / VERDICT N4: an edge whose END point is free but which is blocked at an interior state must still
+    contribute the frame pairs colliding there.  With a zero time budget the planner only checks start -> goal,
+    so the feedback is exactly the oracle's pair set at that edge's first invalid state."""
+    sc = S.baxter_sussman()
+    sg = A.SceneGraph.from_scene(sc)
+    q0 = S.q0_vector(sc)
+    ssg = A.SubSceneGraph(sg, "", SU.FRAME)
+    ids = ssg.config_ids()
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    seg = W.seg_len(lim)
+    sg2 = A.SceneGraph.from_scene(sc)
+    sg2.allow_config(q0)
+    cl = A.Collision(sg2)
+    cand = W.random_configs(lim, 600, seed=14)
+    cand = cand[cl.check_batch(ids, q0, cand)]
+    start = np.repeat(q0[ids][None, :], len(cand), axis=0)
+    valid, first = cl.check_edges(ids, q0, start, cand, seg)
+    blocked = np.nonzero(~valid & (first > 0))[0]
+    assert blocked.size >= 3, "no sampled goal is free with a blocked straight line"
+    orc = O.OracleScene(S.flatten(sc))
+    orc.allow_config(q0)
+    osub = orc.config_ids(S.RIGHT_ARM)
+    checked = 0
+    for e in blocked[:6]:
+        goal = cand[e]
+        est, _, efirst, _ = orc.check_edges(osub, q0, start[e:e + 1], goal[None, :], seg, threads=1)
+        if est[0] != O.HIT or efirst[0] != first[e]:
+            continue  # a contact-band state on the edge: not a clean case
+        mp = A.MotionPlanner(ssg)
+        mp.set_track_collisions(True)
+        mp.set_start(q0)
+        assert mp.set_goal(goal) == 1
+        assert mp.plan(0.0) is None and mp.stats().n_iterations == 0
+        got = set(mp.collisions().pairs())
+        assert got, "an edge blocked at an interior state contributed nothing"
+        # the oracle's pair set at that state
+        nd = max(1, int(np.ceil(np.linalg.norm(goal - start[e]) / seg)))
+        t = O.ompl_order(nd)[first[e] - 1] / nd
+        q = q0.copy()
+        q[ids] = start[e] + (goal - start[e]) * t
+        _, ab = orc.fk(q)
+        st, _, ps = orc.check(ab, want_set=True)
+        want = {(i, j) for i in range(len(ps)) for j in range(i) if ps[i, j] == O.HIT or ps[j, i] == O.HIT}
+        band = {(i, j) for i in range(len(ps)) for j in range(i) if ps[i, j] == O.BAND or ps[j, i] == O.BAND}
+        assert want and want <= got <= (want | band), (want, got)
+        checked += 1
+    assert checked >= 1
+
+
+def test_simplifier_never_lengthens_and_stays_valid(built):
+    """:simplify t = OMPL's reduceVertices -> shortcutPath order (mp.c simplify_path): for the same query and seed the
+    simplified path is valid, ends where the raw one ends, and is no longer than it"""
+    sc = S.baxter_sussman()
+    sg = A.SceneGraph.from_scene(sc)
+    q0 = S.q0_vector(sc)
+    ssg = A.SubSceneGraph(sg, "", SU.FRAME)
+    ids = ssg.config_ids()
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    sg2 = A.SceneGraph.from_scene(sc)
+    sg2.allow_config(q0)
+    cl = A.Collision(sg2)
+    cand = W.random_configs(lim, 300, seed=15)
+    cand = cand[cl.check_batch(ids, q0, cand)]
+    start = np.repeat(q0[ids][None, :], len(cand), axis=0)
+    valid, _ = cl.check_edges(ids, q0, start, cand, W.seg_len(lim))
+    done = 0
+    for goal in cand[~valid][:12]:
+        paths = []
+        for simplify in (False, True):
+            mp = A.MotionPlanner(ssg)
+            mp.set_seed(5)
+            mp.set_simplify(simplify)
+            mp.set_start(q0)
+            assert mp.set_goal(goal) == 1
+            paths.append(mp.plan(1.0))
+        raw, simp = paths
+        if raw is None or simp is None:
+            continue  # the goal lies in another component of the free space
+        length = lambda p: float(np.linalg.norm(np.diff(p[:, ids], axis=0), axis=1).sum())
+        np.testing.assert_array_equal(simp[0], raw[0])
+        np.testing.assert_array_equal(simp[-1], raw[-1])
+        assert length(simp) <= length(raw) + 1e-9
+        assert length(simp) >= np.linalg.norm(goal - q0[ids]) - 1e-9
+        _validate_path(sc, simp, S.RIGHT_ARM)
+        done += 1
+    assert done >= 3
+
+
 def test_c_executor_replays_the_plan(built, tmp_path):
     """the whole boundary in C: a scene plugin generated as C source (what the reference's aarxc emits,
     Makefile.am:213-231), loaded with aa_rx_dl_sg, the start file and the plan file read with

@@ -46,7 +46,7 @@ struct aa_rx_mp {
     int simplify, track;
     uint64_t rng;
     size_t n_blocked;
-    double *blocked; /* end points of rejected extensions (for the collision feed-back) */
+    double *blocked; /* the first invalid state of every rejected edge (for the collision feed-back) */
     struct tmk_mp_stats st;
     int log_on;          /* measurement aid: keep every checked edge so that a CPU baseline can replay them */
     size_t log_n, log_cap;
@@ -257,6 +257,37 @@ int aa_rx_mp_set_wsgoal(struct aa_rx_mp *mp, const double *E7) {
 }
 
 /* ------------------------------------------------------------------ RRT-Connect, frontier-parallel */
+static void remember_blocked(struct aa_rx_mp *mp, const double *q) {
+    if (mp->n_blocked < MP_MAX_BLOCKED) memcpy(mp->blocked + (mp->n_blocked++) * mp->n_sub, q, sizeof(double) * mp->n_sub);
+}
+
+/* k-th (0-based) interior index OMPL's checkMotion tests on an edge of nd segments: FIFO bisection of 1 .. nd-1
+ * (the device restatement is ompl_mid in dev_math.cuh) */
+static int ompl_mid_host(int nd, int k) {
+    int *qa = (int *)malloc(sizeof(int) * 2 * (size_t)(nd + 2)), head = 0, tail = 0, mid = 1;
+    qa[tail++] = 1; qa[tail++] = nd - 1;
+    for (int it = 0; it <= k && head < tail; it++) {
+        const int a = qa[head++], b = qa[head++];
+        mid = (a + b) / 2;
+        if (a < mid) { qa[tail++] = a; qa[tail++] = mid - 1; }
+        if (mid < b) { qa[tail++] = mid + 1; qa[tail++] = b; }
+    }
+    free(qa);
+    return mid;
+}
+
+/* the state at position `pos` of OMPL's test order on the edge a -> b (0 = the end state b) */
+static void edge_state(const struct aa_rx_mp *mp, const double *a, const double *b, int pos, double *out) {
+    const size_t dim = mp->n_sub;
+    if (pos <= 0) { memcpy(out, b, sizeof(double) * dim); return; }
+    double s = 0;
+    for (size_t k = 0; k < dim; k++) s += (b[k] - a[k]) * (b[k] - a[k]);
+    int nd = (int)ceil(sqrt(s) / mp->seg_len);
+    if (nd < 1) nd = 1;
+    const double t = (double)ompl_mid_host(nd, pos - 1) / (double)nd;
+    for (size_t k = 0; k < dim; k++) out[k] = a[k] + (b[k] - a[k]) * t;
+}
+
 static size_t check_edges(struct aa_rx_mp *mp, size_t n_edge, const double *Q0, const double *Q1, uint32_t *bits) {
     mp->st.n_edge_calls++;
     mp->st.n_edges_checked += n_edge;
@@ -270,53 +301,204 @@ static size_t check_edges(struct aa_rx_mp *mp, size_t n_edge, const double *Q0, 
         memcpy(mp->log_q1 + mp->log_n * mp->n_sub, Q1, sizeof(double) * n_edge * mp->n_sub);
         mp->log_n += n_edge;
     }
-    return aa_rx_cl_check_edges(mp->cl, n_edge, mp->n_sub, mp->ids, mp->n_all, mp->q_start_all, Q0, Q1, mp->n_sub, mp->seg_len,
-                                bits, NULL);
-}
-
-static void remember_blocked(struct aa_rx_mp *mp, const double *q) {
-    if (mp->n_blocked < MP_MAX_BLOCKED) memcpy(mp->blocked + (mp->n_blocked++) * mp->n_sub, q, sizeof(double) * mp->n_sub);
-}
-
-/* path: n x dim; returns the new length (shortest path over the vertices through valid straight edges) */
-static size_t shortcut(struct aa_rx_mp *mp, double *path, size_t n) {
-    const size_t dim = mp->n_sub;
-    if (n < 3) return n;
-    if (n > 96) return n; /* long raw paths are rare with range = 20 % of the extent */
-    size_t n_e = 0;
-    double *Q0 = (double *)malloc(sizeof(double) * dim * n * n / 2 + 8), *Q1 = (double *)malloc(sizeof(double) * dim * n * n / 2 + 8);
-    int *ei = (int *)malloc(sizeof(int) * n * n), *ej = (int *)malloc(sizeof(int) * n * n);
-    for (size_t i = 0; i < n; i++)
-        for (size_t j = i + 2; j < n; j++) {
-            memcpy(Q0 + n_e * dim, path + i * dim, sizeof(double) * dim);
-            memcpy(Q1 + n_e * dim, path + j * dim, sizeof(double) * dim);
-            ei[n_e] = (int)i; ej[n_e] = (int)j;
-            n_e++;
+    if (!mp->track || mp->n_blocked >= MP_MAX_BLOCKED)
+        return aa_rx_cl_check_edges(mp->cl, n_edge, mp->n_sub, mp->ids, mp->n_all, mp->q_start_all, Q0, Q1, mp->n_sub,
+                                    mp->seg_len, bits, NULL);
+    /* :track-collisions (lisp/python/tmsmtpy.lisp:59): remember the state that actually blocked every rejected
+     * edge - the first invalid one in OMPL's test order, which may be an interior state of an edge whose end point
+     * is free - so that aa_rx_mp_collisions can report the frame pairs colliding there */
+    int32_t *first = (int32_t *)malloc(sizeof(int32_t) * (n_edge + 1));
+    const size_t bad = aa_rx_cl_check_edges(mp->cl, n_edge, mp->n_sub, mp->ids, mp->n_all, mp->q_start_all, Q0, Q1, mp->n_sub,
+                                            mp->seg_len, bits, first);
+    double q[TMK_MP_MAXSUB];
+    for (size_t e = 0; e < n_edge && bad; e++)
+        if (first[e] >= 0) {
+            edge_state(mp, Q0 + e * mp->n_sub, Q1 + e * mp->n_sub, first[e], q);
+            remember_blocked(mp, q);
         }
-    uint32_t *bits = (uint32_t *)calloc(n_e / 32 + 2, sizeof(uint32_t));
-    check_edges(mp, n_e, Q0, Q1, bits);
-    /* DP over the DAG: consecutive edges are known valid */
-    double *cost = (double *)malloc(sizeof(double) * n);
-    int *prev = (int *)malloc(sizeof(int) * n);
-    for (size_t j = 0; j < n; j++) { cost[j] = INFINITY; prev[j] = -1; }
-    cost[0] = 0;
-    for (size_t j = 1; j < n; j++) {
-        double c = cost[j - 1] + dist(path + (j - 1) * dim, path + j * dim, dim);
-        if (c < cost[j]) { cost[j] = c; prev[j] = (int)j - 1; }
-        for (size_t e = 0; e < n_e; e++)
-            if ((size_t)ej[e] == j && ((bits[e >> 5] >> (e & 31)) & 1u)) {
-                double c2 = cost[ei[e]] + dist(path + (size_t)ei[e] * dim, path + j * dim, dim);
-                if (c2 < cost[j]) { cost[j] = c2; prev[j] = ei[e]; }
+    free(first);
+    return bad;
+}
+
+/* Path simplification in the order of OMPL's PathSimplifier::simplify (what :simplify t asks for): first
+ * reduceVertices - drop vertices whose neighbours can be joined directly -, then shortcutPath - join points ON
+ * the path's segments -, then a final check of the whole path.  Both stages are batched: where OMPL tries one
+ * random shortcut at a time, every candidate of a round goes through one aa_rx_cl_check_edges call.
+ *
+ * reduce_vertices: the shortest vertex sub-sequence through valid straight edges (the fixed point reduceVertices
+ * converges to).  All vertex pairs when they fit one call; for long raw paths only pairs at most `window` vertices
+ * apart, repeated until nothing changes (OMPL's rangeRatio plays the same role).  path: n x dim, returns the new n. */
+#define MP_SHORTCUT_EDGES 8192
+static size_t reduce_vertices(struct aa_rx_mp *mp, double *path, size_t n) {
+    const size_t dim = mp->n_sub;
+    for (int round = 0; round < 8 && n >= 3; round++) {
+        size_t window = n;
+        while (window > 2 && n * window > MP_SHORTCUT_EDGES) window = window * 3 / 4;
+        size_t n_e = 0, cap_e = n * window + 8;
+        double *Q0 = (double *)malloc(sizeof(double) * dim * cap_e), *Q1 = (double *)malloc(sizeof(double) * dim * cap_e);
+        int *ei = (int *)malloc(sizeof(int) * cap_e), *ej = (int *)malloc(sizeof(int) * cap_e);
+        for (size_t i = 0; i < n; i++)
+            for (size_t j = i + 2; j < n && j <= i + window; j++) {
+                memcpy(Q0 + n_e * dim, path + i * dim, sizeof(double) * dim);
+                memcpy(Q1 + n_e * dim, path + j * dim, sizeof(double) * dim);
+                ei[n_e] = (int)i; ej[n_e] = (int)j;
+                n_e++;
             }
+        uint32_t *bits = (uint32_t *)calloc(n_e / 32 + 2, sizeof(uint32_t));
+        if (n_e) check_edges(mp, n_e, Q0, Q1, bits);
+        /* DP over the DAG: consecutive edges are known valid; candidate edges are sorted by i, scanned by j */
+        double *cost = (double *)malloc(sizeof(double) * n);
+        int *prev = (int *)malloc(sizeof(int) * n);
+        for (size_t j = 0; j < n; j++) { cost[j] = INFINITY; prev[j] = -1; }
+        cost[0] = 0;
+        for (size_t j = 1; j < n; j++) {
+            double c = cost[j - 1] + dist(path + (j - 1) * dim, path + j * dim, dim);
+            if (c < cost[j]) { cost[j] = c; prev[j] = (int)j - 1; }
+        }
+        /* edges are generated in increasing i, so cost[i] is final when edge (i, j) relaxes j (Dijkstra order on a DAG) */
+        for (size_t e = 0; e < n_e; e++)
+            if ((bits[e >> 5] >> (e & 31)) & 1u) {
+                const size_t i = (size_t)ei[e], j = (size_t)ej[e];
+                const double c2 = cost[i] + dist(path + i * dim, path + j * dim, dim);
+                if (c2 < cost[j]) {
+                    cost[j] = c2; prev[j] = (int)i;
+                    for (size_t k = j + 1; k < n; k++) { /* the chain of consecutive edges behind j */
+                        const double c = cost[k - 1] + dist(path + (k - 1) * dim, path + k * dim, dim);
+                        if (c < cost[k]) { cost[k] = c; prev[k] = (int)k - 1; } else break;
+                    }
+                }
+            }
+        int *keep = (int *)malloc(sizeof(int) * n);
+        size_t m = 0;
+        for (int v = (int)n - 1; v >= 0; v = prev[v]) { keep[m++] = v; if (v == 0) break; }
+        double *out = (double *)malloc(sizeof(double) * n * dim);
+        for (size_t k = 0; k < m; k++) memcpy(out + k * dim, path + (size_t)keep[m - 1 - k] * dim, sizeof(double) * dim);
+        memcpy(path, out, sizeof(double) * m * dim);
+        free(out); free(keep); free(cost); free(prev); free(bits); free(Q0); free(Q1); free(ei); free(ej);
+        const int done = m == n || window >= n; /* all pairs were tried, or nothing moved */
+        n = m;
+        if (done) break;
     }
-    int *keep = (int *)malloc(sizeof(int) * n);
-    size_t m = 0;
-    for (int v = (int)n - 1; v >= 0; v = prev[v]) { keep[m++] = v; if (v == 0) break; }
-    double *out = (double *)malloc(sizeof(double) * n * dim);
-    for (size_t k = 0; k < m; k++) memcpy(out + k * dim, path + (size_t)keep[m - 1 - k] * dim, sizeof(double) * dim);
-    memcpy(path, out, sizeof(double) * m * dim);
-    free(out); free(keep); free(cost); free(prev); free(bits); free(Q0); free(Q1); free(ei); free(ej);
-    return m;
+    return n;
+}
+
+/* point at arc length d along the polyline (cum[i] = length up to vertex i); returns the segment index */
+static size_t point_at(const double *path, const double *cum, size_t n, size_t dim, double d, double *out) {
+    size_t i = 0;
+    while (i + 2 < n && cum[i + 1] <= d) i++;
+    const double len = cum[i + 1] - cum[i];
+    const double t = len > 0 ? fmin(1.0, fmax(0.0, (d - cum[i]) / len)) : 0.0;
+    for (size_t k = 0; k < dim; k++) out[k] = path[i * dim + k] + t * (path[(i + 1) * dim + k] - path[i * dim + k]);
+    return i;
+}
+
+/* shortcut_path: MP_K random pairs of points on the path per round (the second within a third of the path length
+ * of the first, OMPL's rangeRatio 0.33), one batched check, the non-overlapping valid ones applied by decreasing
+ * saving.  *path may be reallocated (every applied shortcut adds up to two vertices).  Returns the new n. */
+static size_t shortcut_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
+    const size_t dim = mp->n_sub;
+    double *P0 = (double *)malloc(sizeof(double) * MP_K * dim), *P1 = (double *)malloc(sizeof(double) * MP_K * dim);
+    double d0[MP_K], d1[MP_K], save[MP_K];
+    uint32_t bits[MP_K / 32 + 2];
+    for (int round = 0; round < 4 && n >= 3; round++) {
+        double *path = *path_io;
+        double *cum = (double *)malloc(sizeof(double) * n);
+        cum[0] = 0;
+        for (size_t i = 1; i < n; i++) cum[i] = cum[i - 1] + dist(path + (i - 1) * dim, path + i * dim, dim);
+        const double L = cum[n - 1];
+        if (!(L > 0)) { free(cum); break; }
+        int n_c = 0;
+        for (int k = 0; k < MP_K; k++) {
+            double a = rng_unit(&mp->rng) * L, b = a + (0.02 + 0.31 * rng_unit(&mp->rng)) * L;
+            if (b > L) b = L;
+            const size_t sa = point_at(path, cum, n, dim, a, P0 + n_c * dim), sb = point_at(path, cum, n, dim, b, P1 + n_c * dim);
+            if (sa == sb) continue; /* both on one segment: nothing to gain */
+            const double direct = dist(P0 + n_c * dim, P1 + n_c * dim, dim);
+            if (b - a - direct < 1e-6 * L) continue;
+            d0[n_c] = a; d1[n_c] = b; save[n_c] = b - a - direct;
+            n_c++;
+        }
+        int applied = 0;
+        if (n_c) {
+            check_edges(mp, (size_t)n_c, P0, P1, bits);
+            /* greedy: largest saving first, intervals must not overlap */
+            int order[MP_K], n_ok = 0, take[MP_K], n_take = 0;
+            for (int k = 0; k < n_c; k++)
+                if ((bits[k >> 5] >> (k & 31)) & 1u) order[n_ok++] = k;
+            for (int x = 1; x < n_ok; x++) { /* insertion sort by saving, descending */
+                int v = order[x], y = x;
+                while (y > 0 && save[order[y - 1]] < save[v]) { order[y] = order[y - 1]; y--; }
+                order[y] = v;
+            }
+            for (int x = 0; x < n_ok; x++) {
+                const int k = order[x];
+                int clash = 0;
+                for (int y = 0; y < n_take; y++) clash |= !(d1[k] <= d0[take[y]] || d0[k] >= d1[take[y]]);
+                if (!clash) take[n_take++] = k;
+            }
+            if (n_take) {
+                for (int x = 1; x < n_take; x++) { /* by position along the path */
+                    int v = take[x], y = x;
+                    while (y > 0 && d0[take[y - 1]] > d0[v]) { take[y] = take[y - 1]; y--; }
+                    take[y] = v;
+                }
+                double *out = (double *)malloc(sizeof(double) * dim * (n + 2 * (size_t)n_take + 2));
+                size_t m = 0, i = 0;
+                for (int x = 0; x < n_take; x++) {
+                    const int k = take[x];
+                    while (i < n && cum[i] <= d0[k]) { memcpy(out + m * dim, path + i * dim, sizeof(double) * dim); m++; i++; }
+                    memcpy(out + m * dim, P0 + k * dim, sizeof(double) * dim); m++;
+                    memcpy(out + m * dim, P1 + k * dim, sizeof(double) * dim); m++;
+                    while (i < n && cum[i] < d1[k]) i++; /* the vertices the shortcut bypasses */
+                }
+                while (i < n) { memcpy(out + m * dim, path + i * dim, sizeof(double) * dim); m++; i++; }
+                /* a shortcut point that coincides with a kept vertex would leave a zero-length edge */
+                size_t w = 1;
+                for (size_t r = 1; r < m; r++) {
+                    if (dist(out + (w - 1) * dim, out + r * dim, dim) > 1e-12) {
+                        if (w != r) memmove(out + w * dim, out + r * dim, sizeof(double) * dim);
+                        w++;
+                    } else if (r + 1 == m && w > 1) /* the goal itself: keep it bit for bit */
+                        memmove(out + (w - 1) * dim, out + r * dim, sizeof(double) * dim);
+                }
+                free(*path_io);
+                *path_io = out;
+                n = w;
+                applied = n_take;
+            }
+        }
+        free(cum);
+        if (!applied) break;
+    }
+    free(P0); free(P1);
+    return n;
+}
+
+/* reduceVertices -> shortcutPath -> reduceVertices -> check of the final path (OMPL: checkAndRepair).  Shortcut
+ * end points are new states on old segments: the discretised check of a sub-segment samples other states than the
+ * check of the segment did, so the result is validated once more and the vertex-only result kept if it fails. */
+static size_t simplify_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
+    const size_t dim = mp->n_sub;
+    n = reduce_vertices(mp, *path_io, n);
+    if (n < 3) return n;
+    double *safe = (double *)malloc(sizeof(double) * n * dim);
+    memcpy(safe, *path_io, sizeof(double) * n * dim);
+    const size_t n_safe = n;
+    n = shortcut_path(mp, path_io, n);
+    n = reduce_vertices(mp, *path_io, n);
+    int ok = 1;
+    if (n >= 2) {
+        uint32_t *bits = (uint32_t *)calloc(n / 32 + 2, sizeof(uint32_t));
+        ok = check_edges(mp, n - 1, *path_io, *path_io + dim, bits) == 0;
+        free(bits);
+    }
+    if (!ok) {
+        free(*path_io);
+        *path_io = safe;
+        return n_safe;
+    }
+    free(safe);
+    return n;
 }
 
 int aa_rx_mp_plan(struct aa_rx_mp *mp, double timeout, size_t *n_path, double **path_all) {
@@ -370,7 +552,6 @@ int aa_rx_mp_plan(struct aa_rx_mp *mp, double timeout, size_t *n_path, double **
         int n_new = 0;
         for (int k = 0; k < MP_K; k++) {
             if ((bits[k >> 5] >> (k & 31)) & 1u) new_idx[n_new++] = tree_add(Ta, Q1 + k * dim, near_idx[k]);
-            else if (mp->track) remember_blocked(mp, Q1 + k * dim);
         }
         if (n_new) {
             /* connect: straight segments from the nearest node of the other tree to every new node */
@@ -410,7 +591,10 @@ int aa_rx_mp_plan(struct aa_rx_mp *mp, double timeout, size_t *n_path, double **
         for (int v = found_b; v >= 0; v = T[1].parent[v]) memcpy(path + (k++) * dim, T[1].q + (size_t)v * dim, sizeof(double) * dim);
         if (mp->simplify) {
             double ts = now_s();
-            n = shortcut(mp, path, n);
+            const int track = mp->track;
+            mp->track = 0; /* rejected shortcuts are not obstacles between start and goal */
+            n = simplify_path(mp, &path, n);
+            mp->track = track;
             mp->st.simplify_s += now_s() - ts;
         }
         double *out = (double *)malloc(sizeof(double) * n * mp->n_all);
@@ -428,7 +612,8 @@ int aa_rx_mp_plan(struct aa_rx_mp *mp, double timeout, size_t *n_path, double **
     return rc;
 }
 
-/* frame pairs that blocked extensions: full-report check of the rejected end points */
+/* frame pairs that blocked extensions and connections: full-report check of the first invalid state of every
+ * rejected edge (what the :collision constraint mode consumes, lisp/itmp-rec.lisp:230-247) */
 void aa_rx_mp_collisions(struct aa_rx_mp *mp, struct aa_rx_cl_set *set) {
     if (!mp->cl || mp->n_blocked == 0) return;
     uint32_t *bits = (uint32_t *)calloc(mp->n_blocked / 32 + 2, sizeof(uint32_t));
