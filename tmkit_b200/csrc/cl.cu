@@ -111,7 +111,7 @@ struct PinnedPool { /* 64-byte pinned slots (the counters a batch call reads bac
 };
 static PinnedPool g_pinned_pool;
 
-struct StreamSet { cudaStream_t stream, copy_stream; cudaEvent_t ev[8]; int dev; };
+struct StreamSet { cudaStream_t stream, copy_stream, aux_stream; cudaEvent_t ev[8], ev_aux[4]; int dev; };
 struct StreamPool { /* the two streams and the copy events of a collision context (idle when returned) */
     std::mutex mu;
     std::vector<StreamSet> free_;
@@ -132,7 +132,9 @@ struct StreamPool { /* the two streams and the copy events of a collision contex
         ss.dev = dev;
         CK(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ss.copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ss.aux_stream, cudaStreamNonBlocking));
         for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&ss.ev[k], cudaEventDisableTiming));
+        for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&ss.ev_aux[k], cudaEventDisableTiming));
         return ss;
     }
     void give(const StreamSet &ss) { std::lock_guard<std::mutex> g(mu); free_.push_back(ss); }
@@ -396,7 +398,8 @@ struct aa_rx_cl {
     uint64_t allow_serial;
     cudaStream_t stream;
     cudaStream_t copy_stream; /* host-buffer entry points: H2D of chunk k+1 overlaps the kernels of chunk k */
-    cudaEvent_t ev_copy[8];
+    cudaStream_t aux_stream;  /* the deferred narrowphase forks here: convex items beside the mesh traversal */
+    cudaEvent_t ev_copy[8], ev_aux[4];
 
     /* frame-relative geometry + meshes */
     std::vector<DGeom<double>> geoms;
@@ -549,8 +552,9 @@ extern "C" struct aa_rx_cl *aa_rx_cl_create(const struct aa_rx_sg *sg) {
     memset(&cl->stats, 0, sizeof(cl->stats));
     {
         StreamSet ss = g_stream_pool.take();
-        cl->stream = ss.stream; cl->copy_stream = ss.copy_stream;
+        cl->stream = ss.stream; cl->copy_stream = ss.copy_stream; cl->aux_stream = ss.aux_stream;
         memcpy(cl->ev_copy, ss.ev, sizeof(ss.ev));
+        memcpy(cl->ev_aux, ss.ev_aux, sizeof(ss.ev_aux));
     }
     hs.mark("streams+events");
     cl->h_cnt = (uint32_t *)g_pinned_pool.take();
@@ -578,8 +582,9 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     g_pinned_pool.give(cl->h_cnt);
     {
         StreamSet ss;
-        ss.stream = cl->stream; ss.copy_stream = cl->copy_stream;
+        ss.stream = cl->stream; ss.copy_stream = cl->copy_stream; ss.aux_stream = cl->aux_stream;
         memcpy(ss.ev, cl->ev_copy, sizeof(ss.ev));
+        memcpy(ss.ev_aux, cl->ev_aux, sizeof(ss.ev_aux));
         CK(cudaGetDevice(&ss.dev));
         g_stream_pool.give(ss);
     }
@@ -1056,9 +1061,19 @@ static void launch_tile(const Image<float> &f, const TileCfg &cfg, const Src &sr
  * list is filled by the traversal) */
 template <class Src, class Sink>
 static void launch_heavy(const Image<float> &f, const Src &src, const Sink &sink, const UncList &u, unsigned ctas,
-                         cudaStream_t s, uint32_t *trav_next) {
-    k_conv_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
+                         cudaStream_t s, uint32_t *trav_next, struct aa_rx_cl *cl) {
+    /* the convex items (SAT / GJK) are independent of the mesh chain (traversal -> open triangles): they run
+     * beside it on the context's second stream and rejoin before the exact re-check.  Inside a stream capture the
+     * fork becomes two branches of the graph. */
+    static const bool fork = getenv("TMK_NO_FORK") == nullptr; /* A/B aid */
+    cudaStream_t sc = fork ? cl->aux_stream : s;
+    if (fork) {
+        CK(cudaEventRecord(cl->ev_aux[0], s));
+        CK(cudaStreamWaitEvent(sc, cl->ev_aux[0], 0));
+    }
+    k_conv_items<Src, Sink><<<ctas, 128, 0, sc>>>(f, src, sink, u);
     CK(cudaGetLastError());
+    if (fork) CK(cudaEventRecord(cl->ev_aux[1], sc));
     static const bool simple = getenv("TMK_TRAVERSE_SIMPLE") != nullptr; /* A/B aid */
     static const unsigned trav_ctas = getenv("TMK_TRAV_CTAS") ? (unsigned)atoi(getenv("TMK_TRAV_CTAS")) : 7u;
     if (simple) k_mesh_traverse_simple<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
@@ -1066,17 +1081,19 @@ static void launch_heavy(const Image<float> &f, const Src &src, const Sink &sink
     CK(cudaGetLastError());
     k_tri_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
     CK(cudaGetLastError());
+    if (fork) CK(cudaStreamWaitEvent(s, cl->ev_aux[1], 0));
 }
 
 static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bool reset = true) {
     UncList u;
+    DBuf &b_unc = cl->d_unc, &b_cnt = cl->d_cnt, &b_mesh = cl->d_mesh, &b_conv = cl->d_conv, &b_tri = cl->d_tri;
     u.cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states / 2), 0x7fffffffu);
     if (const char *e = getenv("TMK_UNC_CAP")) u.cap = (uint32_t)std::max(1, atoi(e)); /* test aid: forces k_overflow_all */
-    cl->d_unc.need(sizeof(uint4) * (size_t)u.cap);
-    cl->d_cnt.need(512);
-    u.items = (uint4 *)cl->d_unc.p;
-    u.n = (uint32_t *)cl->d_cnt.p;
-    u.overflow = (uint32_t *)cl->d_cnt.p + 1;
+    b_unc.need(sizeof(uint4) * (size_t)u.cap);
+    b_cnt.need(512);
+    u.items = (uint4 *)b_unc.p;
+    u.n = (uint32_t *)b_cnt.p;
+    u.overflow = (uint32_t *)b_cnt.p + 1;
     /* per-CTA spill area of the broadphase queue (only touched when a shared-memory region fills up) */
     u.spill_cap = 1u << 15;
     if (const char *e = getenv("TMK_SPILL_CAP")) u.spill_cap = (uint32_t)std::max(0, atoi(e)); /* test aid */
@@ -1086,22 +1103,22 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     /* exported mesh items: room for 1.5 per state (more than that: the exact re-check takes them) */
     u.mesh_cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states + n_states / 2), 0x3fffffffu);
     if (const char *e = getenv("TMK_MESH_CAP")) u.mesh_cap = (uint32_t)std::max(0, atoi(e)); /* test aid */
-    cl->d_mesh.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.mesh_cap, 1));
-    u.mesh_items = (float4 *)cl->d_mesh.p;
+    b_mesh.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.mesh_cap, 1));
+    u.mesh_items = (float4 *)b_mesh.p;
     /* d_cnt words: [0] undecided, [1] overflow, [2..3] states, [4] mesh items, [5] convex items, [6] triangles, [7] work counter of k_mesh_traverse, [26..27] tile counter of k_states_tile,
      * [8+L] alive edges of level L, [32+L] / [48+L] / [64+L] mesh / convex / triangle items of edge level L */
-    u.mesh_n = (uint32_t *)cl->d_cnt.p + 4;
+    u.mesh_n = (uint32_t *)b_cnt.p + 4;
     u.conv_cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, n_states), 0x3fffffffu);
     u.tri_cap = u.conv_cap;
     if (const char *e = getenv("TMK_MESH_CAP")) u.conv_cap = u.tri_cap = u.mesh_cap;
-    cl->d_conv.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.conv_cap, 1));
-    cl->d_tri.need(sizeof(uint2) * (size_t)std::max<uint32_t>(u.tri_cap, 1));
-    u.conv_items = (float4 *)cl->d_conv.p;
-    u.conv_n = (uint32_t *)cl->d_cnt.p + 5;
-    u.tri_items = (uint2 *)cl->d_tri.p;
-    u.tri_n = (uint32_t *)cl->d_cnt.p + 6;
-    u.tile_ctr = (uint32_t *)cl->d_cnt.p + 26; /* words 26, 27 */
-    if (reset) CK(cudaMemsetAsync(cl->d_cnt.p, 0, 512, s)); /* after every allocation: capturable */
+    b_conv.need(sizeof(float4) * TMK_MESH_REC * (size_t)std::max<uint32_t>(u.conv_cap, 1));
+    b_tri.need(sizeof(uint2) * (size_t)std::max<uint32_t>(u.tri_cap, 1));
+    u.conv_items = (float4 *)b_conv.p;
+    u.conv_n = (uint32_t *)b_cnt.p + 5;
+    u.tri_items = (uint2 *)b_tri.p;
+    u.tri_n = (uint32_t *)b_cnt.p + 6;
+    u.tile_ctr = (uint32_t *)b_cnt.p + 26; /* words 26, 27 */
+    if (reset) CK(cudaMemsetAsync(b_cnt.p, 0, 512, s)); /* after every allocation: capturable */
     return u;
 }
 
@@ -1175,7 +1192,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         cl->stats.n_launches += 1;
         if (c_end < n_cfg) return;
         src.n = n_cfg; src.s_begin = 0;
-        launch_heavy<SrcConfigs, SinkBits>(im.f, src, sink, u, 148 * 16, s, (uint32_t *)cl->d_cnt.p + 7);
+        launch_heavy<SrcConfigs, SinkBits>(im.f, src, sink, u, 148 * 16, s, (uint32_t *)cl->d_cnt.p + 7, cl);
         if (ev) CK(cudaEventRecord(ev[1], s));
         k_recheck_items<SrcConfigs, SinkBits><<<148 * 3, 128, 0, s>>>(im.d, src, sink, u);
         CK(cudaGetLastError());

@@ -170,6 +170,23 @@ __device__ __forceinline__ void fk_config(const Image<T> &im, const T *q, Xf<T> 
     for (int g = 0; g < im.n_mg; g++) gp[g] = xmul(jp[im.mg[g].slot], xload(im.mg[g].tf));
 }
 
+/* world poses of two moving geometries only (the exact re-check of one pair): the chain is walked as far as the
+ * later of their joints - parents precede children in the joint table - and no other geometry pose is built */
+template <typename T>
+__device__ __forceinline__ void fk_pair(const Image<T> &im, const T *q, int a, int b, Xf<T> &XA, Xf<T> &XB) {
+    Xf<T> jp[TMK_MAXJ];
+    const int sa = im.mg[a].slot, sb = b >= 0 ? im.mg[b].slot : -1;
+    const int last = sa > sb ? sa : sb;
+    for (int j = 0; j <= last; j++) {
+        const DJoint<T> &J = im.joints[j];
+        Xf<T> par;
+        if (J.parent >= 0) par = jp[J.parent];
+        jp[j] = fk_joint(xload(J.E), mk<T>(J.ax[0], J.ax[1], J.ax[2]), J.off, J.type, q[J.qslot], J.parent >= 0 ? &par : nullptr);
+    }
+    XA = xmul(jp[sa], xload(im.mg[a].tf));
+    if (b >= 0) XB = xmul(jp[sb], xload(im.mg[b].tf));
+}
+
 /* validity of one configuration: SEP (free), HIT, UNC.  pairhit != NULL: no early-out, colliding
  * pairs are flagged (the :track-collisions feed-back). */
 template <typename T>

@@ -826,16 +826,16 @@ __global__ void __launch_bounds__(128) k_recheck_items(Image<double> im, Src src
         if (!st.live) continue;
         double q[TMK_MAXSUB];
         for (int k = 0; k < im.n_sub; k++) q[k] = src.template load1<double>(st, k);
-        Xf<double> gp[TMK_MAXMG];
-        fk_config(im, q, gp);
         const int a = ITEM_A(pair), b = ITEM_B(pair);
         const DGeom<double> &A = im.mg[a];
         const DGeom<double> &B = ITEM_STATIC(pair) ? im.sg[b] : im.mg[b];
-        const Xf<double> XB = ITEM_STATIC(pair) ? xload(B.tf) : gp[b];
+        Xf<double> XA, XB;
+        fk_pair(im, q, a, ITEM_STATIC(pair) ? -1 : b, XA, XB); /* only the joints these two geometries hang on */
+        if (ITEM_STATIC(pair)) XB = xload(B.tf);
         int r;
-        if (it.w == TMK_WHOLE_PAIR) r = test_geoms(A, gp[a], B, XB, im.meshes);
-        else if (A.shape == K_MESH) r = test_mesh_tri_shape(im.meshes[A.mesh], gp[a], shape_of(B), XB, (int)it.w);
-        else r = test_mesh_tri_shape(im.meshes[B.mesh], XB, shape_of(A), gp[a], (int)it.w);
+        if (it.w == TMK_WHOLE_PAIR) r = test_geoms(A, XA, B, XB, im.meshes);
+        else if (A.shape == K_MESH) r = test_mesh_tri_shape(im.meshes[A.mesh], XA, shape_of(B), XB, (int)it.w);
+        else r = test_mesh_tri_shape(im.meshes[B.mesh], XB, shape_of(A), XA, (int)it.w);
         if (r == HIT) sink.mark_hit(st);
     }
 }
