@@ -469,6 +469,45 @@ def test_dual_arm_clutter_scene(n_prims, reject):
     _assert_verdicts(ev, est, "dual-arm clutter edges", max_band_frac=0.05)
 
 
+def test_wavefront_pipeline_equals_the_tile_kernel(monkeypatch):
+    """large scenes run the wavefront kernels (wave.cuh: FK / broadphase / quick certificates / export as separate
+    full-occupancy launches) instead of the tile kernel: same tests, same arithmetic, the same bits - also through
+    the host-buffer call (chunked), across its chunk boundary, and when its queues overflow"""
+    import torch
+    sc = S.clutter_scene(512, seed=0)
+    q0 = S.q0_vector(sc)
+    names = S.RIGHT_ARM + S.LEFT_ARM
+    lim = W.arm_limit_table(names)
+    sg, cl, _ = _gpu_scene(sc, q0)
+    sub = sg.config_indices(names)
+    n = (1 << 20) + 5000 + 17  # more than one wavefront chunk, ragged
+    Q = W.random_configs(lim, n, seed=41)
+    dq = torch.from_numpy(np.ascontiguousarray(Q.T.astype(np.float32))).cuda()
+    nw = (n + 31) // 32
+    got = {}
+    for mode in ("wave", "tile"):
+        if mode == "tile":
+            monkeypatch.setenv("TMK_NO_WAVE_NOW", "1")
+        bits = torch.full((nw + 8,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        for _ in range(3):  # the third call replays the library's graph
+            cl.check_batch_dev(n, sub, q0, dq.data_ptr(), A.Q_SOA_F32, n, bits.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        h = bits.cpu().numpy().view(np.uint32)
+        assert (h[nw:] == 0x5A5A5A5A).all()
+        got[mode] = A.Collision.unpack_bits(h[:nw].copy(), n)
+        got[mode + "_host"] = cl.check_batch(sub, q0, Q[:400_000])
+    assert np.array_equal(got["wave"], got["tile"])
+    assert np.array_equal(got["wave_host"], got["tile_host"]) and np.array_equal(got["wave_host"], got["wave"][:400_000])
+    assert 0.01 < got["wave"].mean() < 0.5
+    monkeypatch.delenv("TMK_NO_WAVE_NOW")
+    orc = _oracle_scene(sc, q0)
+    st, _ = orc.check_batch(orc.config_ids(names), q0, Q[:3000], threads=CORES, early_out=True)
+    _assert_verdicts(got["wave"][:3000], st, "wavefront pipeline")
+    # queues too small for the survivors: the overflow flag sends every state through the exact kernel
+    monkeypatch.setenv("TMK_WAVE_QCAP", "500")
+    assert np.array_equal(cl.check_batch(sub, q0, Q[:6000]), got["wave"][:6000])
+
+
 def test_static_grid_equals_brute_force(monkeypatch):
     """large scenes put their small static geometry into a uniform grid; the pair-list sweep (grid off)
     must give the same bits - configurations and edges, obstacles of every size class."""

@@ -20,6 +20,7 @@
 
 #include "kernels.cuh"
 #include "pipeline.cuh"
+#include "wave.cuh"
 #include "ik.cuh"
 #include "tmk_internal.h"
 
@@ -377,7 +378,7 @@ extern "C" void tmk_mesh_compiled_release(void *compiled) { delete (HostMesh *)c
 
 /* ------------------------------------------------------------------ the collision context */
 struct ImageDev {
-    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, g_cells, g_items, g_live;
+    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, g_cells, g_items, g_live, g_c4;
     Image<float> f;
     Image<double> d;
     std::vector<uint32_t> h_pairs;
@@ -415,6 +416,7 @@ struct aa_rx_cl {
 
     /* batch scratch */
     DBuf d_spill, d_mesh, d_conv, d_tri;
+    DBuf d_wpose, d_whit, d_wqueue, d_wpend; /* wavefront pipeline of large scenes (wave.cuh) */
     DBuf d_q, d_q1, d_bits, d_unc, d_cnt, d_first, d_pairhit, d_stats, d_nd, d_alive0, d_alive1, d_efirst;
     uint32_t *h_cnt; /* pinned */
     int track, stats_on;
@@ -572,10 +574,10 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     if (cur_dev != cl->dev) cudaSetDevice(cl->dev); /* buffers and streams go back to the pools of their device */
     cudaDeviceSynchronize(); /* the scratch buffers go back to the pool: nothing may still use them */
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
-                    &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_conv, &cl->d_tri, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
+                    &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_conv, &cl->d_tri, &cl->d_wpose, &cl->d_whit, &cl->d_wqueue, &cl->d_wpend, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
                     &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4, &cl->img.tpairs, &cl->img.g_cells, &cl->img.g_items,
-                    &cl->img.g_live};
+                    &cl->img.g_live, &cl->img.g_c4};
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     for (auto &g : cl->edge_graphs) cudaGraphExecDestroy(g.exec);
@@ -981,6 +983,15 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     upload(im.g_items, cell_items, cl->stream);
     upload(im.g_live, live_ms, cl->stream);
     {
+        std::vector<float4> cell_c4(cell_items.size() + 1);
+        for (size_t k = 0; k < cell_items.size(); k++) {
+            const SQuick &Q = sq.empty() ? SQuick() : sq[std::min<size_t>(cell_items[k], sq.size() - 1)];
+            cell_c4[k] = make_float4(Q.cx, Q.cy, Q.cz, Q.brad);
+        }
+        cell_c4[cell_items.size()] = make_float4(0.f, 0.f, 0.f, 0.f);
+        upload(im.g_c4, cell_c4, cl->stream);
+    }
+    {
         std::vector<float4> ps4(tpairs.size() + 1);
         for (size_t k = 0; k < tpairs.size(); k++) {
             uint32_t w = tpairs[k].w;
@@ -1014,6 +1025,8 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     grid.cell_start = (const int *)im.g_cells.p;
     grid.items = (const unsigned short *)im.g_items.p;
     grid.live = (const uint32_t *)im.g_live.p;
+    grid.c4 = (const float4 *)im.g_c4.p;
+    grid.n_items = grid.on ? (int)n_gridded : 0;
     im.d.grid = im.f.grid = grid;
     if (grid.on) {
         tile_configure(im.wcfg, im.f, n_jslab, k_states_tile<SrcConfigs, SinkBits, 256, true>,
@@ -1122,6 +1135,62 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     return u;
 }
 
+/* ---- large scenes: the wavefront pipeline (wave.cuh) instead of the tile kernel ---- */
+#define TMK_WAVE_CHUNK (size_t(1) << 20)
+static bool wave_wanted(const struct aa_rx_cl *cl, size_t n_states) {
+    static const bool off = getenv("TMK_NO_WAVE") != nullptr; /* A/B aid and test hook */
+    return cl->img.f.grid.on && n_states >= 4096 && !off && !getenv("TMK_NO_WAVE_NOW");
+}
+static WaveBuf wave_buffers(struct aa_rx_cl *cl, size_t n_states) {
+    WaveBuf w;
+    const size_t cap = std::min(n_states, TMK_WAVE_CHUNK);
+    const size_t capr = (cap + 31) & ~(size_t)31;
+    w.cap = (uint32_t)capr;
+    cl->d_wpose.need(sizeof(float) * 7 * (size_t)std::max(1, cl->img.f.n_mg) * capr);
+    cl->d_whit.need(capr);
+    w.queue_cap = (uint32_t)std::min<size_t>(capr * 64, 0x7ffffff0u);
+    w.pend_cap = (uint32_t)std::min<size_t>(capr * 8, 0x7ffffff0u);
+    if (const char *e = getenv("TMK_WAVE_QCAP")) w.queue_cap = w.pend_cap = (uint32_t)std::max(1, atoi(e)); /* test aid */
+    cl->d_wqueue.need(sizeof(uint2) * (size_t)w.queue_cap);
+    cl->d_wpend.need(sizeof(uint2) * (size_t)w.pend_cap);
+    w.pose = (float *)cl->d_wpose.p;
+    w.hit = (uint8_t *)cl->d_whit.p;
+    w.queue = (uint2 *)cl->d_wqueue.p;
+    w.pend = (uint2 *)cl->d_wpend.p;
+    w.counters = nullptr; /* set by the caller: words 16, 17 of the batch's counter block */
+    return w;
+}
+/* states [begin, end) of the batch at dQ through the wavefront kernels; exported items join the batch's lists */
+static size_t launch_wave(struct aa_rx_cl *cl, const void *dQ, int layout, size_t ld, size_t begin, size_t end,
+                          uint32_t *d_bits, const UncList &u, cudaStream_t s) {
+    ImageDev &im = cl->img;
+    WaveBuf w = wave_buffers(cl, end - begin);
+    w.counters = u.n + 16;
+    const StaticGrid &G = im.f.grid;
+    const size_t n_cell = (size_t)G.nx * G.ny * G.nz + 1;
+    const size_t smem = sizeof(uint2) * 8 * TMK_WAVE_STAGE + sizeof(int) * ((n_cell + 3) & ~(size_t)3) + (size_t)G.n_items * 18 + 64;
+    if (smem > 160 * 1024) tmk_die("batch: the static grid (%zu cells, %d items) does not fit the broadphase kernel's shared memory", n_cell, G.n_items);
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(k_wave_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    size_t launches = 0;
+    for (size_t c0 = begin; c0 < end; c0 += TMK_WAVE_CHUNK) {
+        const size_t c1 = std::min(end, c0 + TMK_WAVE_CHUNK);
+        const uint32_t n = (uint32_t)(c1 - c0);
+        SrcConfigs src;
+        src.p = dQ; src.layout = layout; src.ld = ld; src.n = n; src.s_begin = c0;
+        CK(cudaMemsetAsync(w.counters, 0, 8, s));
+        const unsigned gx = (n + 255) / 256;
+        k_wave_fk<SrcConfigs><<<gx, 256, 0, s>>>(im.f, src, w);
+        k_wave_broad<<<dim3(gx, (unsigned)im.f.n_mg), 256, smem, s>>>(im.f, w, n, u, c0);
+        k_wave_quick<<<148 * 8, 256, 0, s>>>(im.f, w, u, c0);
+        k_wave_export<<<148 * 4, 256, 0, s>>>(im.f, w, u, c0);
+        k_wave_bits<<<gx, 256, 0, s>>>(w, n, d_bits + c0 / 32);
+        CK(cudaGetLastError());
+        launches += 5;
+    }
+    return launches;
+}
+
 /* the caller may be capturing the stream into a graph of its own: then no nested capture / replay */
 static bool stream_is_capturing(cudaStream_t s) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -1154,10 +1223,12 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         if (use_graph) {
             UncList u0 = unc_list(cl, n_cfg, s, false); /* allocations happen outside the capture */
             (void)u0;
+            if (wave_wanted(cl, n_cfg)) (void)wave_buffers(cl, n_cfg);
             const uint64_t k0[12] = {(uint64_t)n_cfg | (1ull << 62), (uint64_t)(uintptr_t)dQ, 0, (uint64_t)layout * 1315423911u + ld, 0,
                                      (uint64_t)(uintptr_t)d_bits, 0, (uint64_t)(uintptr_t)s, im.serial,
                                      (uint64_t)(uintptr_t)cl->d_unc.p ^ ((uint64_t)(uintptr_t)cl->d_mesh.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_conv.p << 2),
-                                     0, (uint64_t)(uintptr_t)cl->d_spill.p ^ ((uint64_t)(uintptr_t)cl->d_tri.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_cnt.p << 2)};
+                                     (uint64_t)(uintptr_t)cl->d_wpose.p ^ ((uint64_t)(uintptr_t)cl->d_wqueue.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_wpend.p << 2) ^ ((uint64_t)(uintptr_t)cl->d_whit.p << 3),
+                                     (uint64_t)(uintptr_t)cl->d_spill.p ^ ((uint64_t)(uintptr_t)cl->d_tri.p << 1) ^ ((uint64_t)(uintptr_t)cl->d_cnt.p << 2)};
             memcpy(key, k0, sizeof(key));
             for (auto &g : cl->edge_graphs)
                 if (0 == memcmp(g.key, key, sizeof(key))) {
@@ -1187,9 +1258,11 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         const int T = im.wcfg.tile;
         unsigned grid = (unsigned)std::min<size_t>((src.n + T - 1) / T, (size_t)im.wcfg.grid);
         cudaEvent_t *ev = chunk_begin == 0 ? (cl->cur_ev = timing_begin(cl, s)) : cl->cur_ev;
-        launch_tile<SrcConfigs, SinkBits>(im.f, im.wcfg, src, sink, u, (unsigned long long *)nullptr, grid, s);
+        size_t n_main = 1;
+        if (wave_wanted(cl, c_end - chunk_begin)) n_main = launch_wave(cl, dQ, layout, ld, chunk_begin, c_end, d_bits, u, s);
+        else launch_tile<SrcConfigs, SinkBits>(im.f, im.wcfg, src, sink, u, (unsigned long long *)nullptr, grid, s);
         CK(cudaGetLastError());
-        cl->stats.n_launches += 1;
+        cl->stats.n_launches += n_main;
         if (c_end < n_cfg) return;
         src.n = n_cfg; src.s_begin = 0;
         launch_heavy<SrcConfigs, SinkBits>(im.f, src, sink, u, 148 * 16, s, (uint32_t *)cl->d_cnt.p + 7, cl);
@@ -1208,7 +1281,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
             CK(cudaGraphInstantiate(&g.exec, graph, 0));
             CK(cudaGraphDestroy(graph));
             g.used = ++cl->graph_clock;
-            g.n_kernels = 6;
+            g.n_kernels = n_main + 5;
             if (cl->edge_graphs.size() >= 16) { /* replace the least recently used */
                 size_t lru = 0;
                 for (size_t k = 1; k < cl->edge_graphs.size(); k++)

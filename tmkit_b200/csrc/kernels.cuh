@@ -55,6 +55,9 @@ struct StaticGrid {
     float ox, oy, oz, inv_h, r_max;
     const int *cell_start;         /* [nx*ny*nz + 1] */
     const unsigned short *items;   /* static geometry indices, cell by cell */
+    const float4 *c4;              /* bounding centre + radius of items[k], in the same (cell) order: the walk reads
+                                    * this array front to back and touches nothing else until a sphere test passes */
+    int n_items;
     const uint32_t *live;          /* [n_mg][wps] bit b: pair (a, static b) is a candidate (not allowed-away, reachable) */
     int wps;
 };

@@ -40,6 +40,7 @@ struct TileCfg {
     int stage; /* 1: image staged in shared memory */
     int off_joint, off_mg, off_sg, off_pairs, off_sq, off_jg, off_pa, off_ps4;
     int bytes_joint, bytes_mg, bytes_sg, bytes_pairs, bytes_sq, bytes_jg, bytes_pa, bytes_ps4;
+    int off_gcell, off_gitems, off_gc4, bytes_gcell, bytes_gitems, bytes_gc4; /* static grid (large scenes) */
     int off_slab, off_qs, off_jslab, off_q1, off_q2, off_q3, off_flags, off_unc;
     int q1_cap, q2_cap, q3_cap;
     int tile; /* threads per CTA = states per pass: 256 or 128 */
@@ -271,6 +272,9 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
     const SQuick *SQ = (const SQuick *)im.sq;
     const int *JG = im.jg_begin, *PA = im.pa_begin;
     const float4 *PS4 = (const float4 *)im.ps4;
+    const int *GCELL = im.grid.cell_start;
+    const unsigned short *GITEMS = im.grid.items;
+    const float4 *GC4 = im.grid.c4;
 
     if (cfg.stage) {
         if (tid == 0) {
@@ -281,6 +285,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         if (tid == 0) {
             uint32_t total = (uint32_t)(cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_sg + cfg.bytes_pairs + cfg.bytes_sq +
                                         cfg.bytes_jg + cfg.bytes_pa + cfg.bytes_ps4);
+            if (GRID) total += (uint32_t)(cfg.bytes_gcell + cfg.bytes_gitems + cfg.bytes_gc4);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(total)
                          : "memory");
             bulk_g2s(smem + cfg.off_joint, im.joints, (uint32_t)cfg.bytes_joint, &bar);
@@ -291,6 +296,11 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
             bulk_g2s(smem + cfg.off_jg, im.jg_begin, (uint32_t)cfg.bytes_jg, &bar);
             bulk_g2s(smem + cfg.off_pa, im.pa_begin, (uint32_t)cfg.bytes_pa, &bar);
             if (cfg.bytes_ps4) bulk_g2s(smem + cfg.off_ps4, im.ps4, (uint32_t)cfg.bytes_ps4, &bar);
+            if (GRID && cfg.bytes_gcell) {
+                bulk_g2s(smem + cfg.off_gcell, im.grid.cell_start, (uint32_t)cfg.bytes_gcell, &bar);
+                bulk_g2s(smem + cfg.off_gitems, im.grid.items, (uint32_t)cfg.bytes_gitems, &bar);
+                bulk_g2s(smem + cfg.off_gc4, im.grid.c4, (uint32_t)cfg.bytes_gc4, &bar);
+            }
         }
         uint32_t done = 0;
         while (!done) {
@@ -307,6 +317,11 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
         JG = (const int *)(smem + cfg.off_jg);
         PA = (const int *)(smem + cfg.off_pa);
         if (cfg.bytes_ps4) PS4 = (const float4 *)(smem + cfg.off_ps4);
+        if (GRID && cfg.bytes_gcell) {
+            GCELL = (const int *)(smem + cfg.off_gcell);
+            GITEMS = (const unsigned short *)(smem + cfg.off_gitems);
+            GC4 = (const float4 *)(smem + cfg.off_gc4);
+        }
     }
 
     float *slab = (float *)(smem + cfg.off_slab);       /* [n_mg*7][TILE] geometry poses */
@@ -485,14 +500,14 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                         for (int z = z0; z <= z1; z++)
                             for (int y = y0; y <= y1; y++) {
                                 const int row = (z * G.ny + y) * G.nx;
-                                const int k1 = G.cell_start[row + x1 + 1];
-                                for (int k = G.cell_start[row + x0]; k < k1; k++) { /* cells x0..x1 of a row are contiguous */
-                                    const int b = G.items[k];
-                                    if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
-                                    const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
+                                const int k1 = GCELL[row + x1 + 1];
+                                for (int k = GCELL[row + x0]; k < k1; k++) { /* cells x0..x1 of a row are contiguous */
+                                    const float4 c4 = GC4[k];
                                     const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
                                     const float reach = ra + c4.w;
                                     if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
+                                    const int b = GITEMS[k]; /* rare from here on */
+                                    if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
                                     const uint32_t idx = atomicAdd(&wn1[warp], 1u);
                                     const uint32_t item = item_pack(tid, a, b, 1);
                                     if (idx < (uint32_t)cfg.q1_cap) q1w[idx] = item;
@@ -941,10 +956,18 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
     cfg.bytes_jg = align16((im.n_joint + 1) * 4);
     cfg.bytes_pa = align16((3 * im.n_mg + 1) * 4);
     cfg.bytes_ps4 = im.n_tpair * 16;
+    /* the static grid's walk arrays: cell starts, item ids, item spheres in cell order */
+    cfg.bytes_gcell = im.grid.on ? align16((im.grid.nx * im.grid.ny * im.grid.nz + 1) * 4) : 0;
+    cfg.bytes_gitems = im.grid.on ? align16((im.grid.n_items + 1) * 2) : 0;
+    cfg.bytes_gc4 = im.grid.on ? (im.grid.n_items + 1) * 16 : 0;
     /* staging policy: everything if it fits the budget; else leave the static geometry table (only read by
      * the narrowphase phases) in global memory; else the quick table too; else nothing */
     {
-        const int small = cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_jg + cfg.bytes_pa;
+        int small = cfg.bytes_joint + cfg.bytes_mg + cfg.bytes_jg + cfg.bytes_pa;
+        /* the grid walk is the inner loop of a large scene: its arrays go first, the quick tables (read once per
+         * surviving pair) last */
+        if (small + cfg.bytes_gcell + cfg.bytes_gitems + cfg.bytes_gc4 <= TMK_STAGE_BUDGET) small += cfg.bytes_gcell + cfg.bytes_gitems + cfg.bytes_gc4;
+        else cfg.bytes_gcell = cfg.bytes_gitems = cfg.bytes_gc4 = 0;
         const int lists = cfg.bytes_pairs + cfg.bytes_ps4;
         cfg.stage = 1;
         if (small + lists + cfg.bytes_sq + cfg.bytes_sg <= TMK_STAGE_BUDGET) { /* all */
@@ -952,6 +975,7 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
         else if (small + lists <= TMK_STAGE_BUDGET) cfg.bytes_sg = cfg.bytes_sq = 0;
         else if (small <= TMK_STAGE_BUDGET) cfg.bytes_sg = cfg.bytes_sq = cfg.bytes_pairs = cfg.bytes_ps4 = 0;
         else cfg.stage = 0;
+        if (!cfg.stage) cfg.bytes_gcell = cfg.bytes_gitems = cfg.bytes_gc4 = 0;
     }
     int off = 0;
     cfg.off_joint = off; off += cfg.stage ? cfg.bytes_joint : 0;
@@ -962,6 +986,9 @@ static int tile_plan(TileCfg &cfg, const Image<float> &im, int n_jslab, Kernel k
     cfg.off_jg = off; off += cfg.stage ? cfg.bytes_jg : 0;
     cfg.off_pa = off; off += cfg.stage ? cfg.bytes_pa : 0;
     cfg.off_ps4 = off; off += cfg.stage ? cfg.bytes_ps4 : 0;
+    cfg.off_gcell = off; off += cfg.bytes_gcell;
+    cfg.off_gitems = off; off += cfg.bytes_gitems;
+    cfg.off_gc4 = off; off += cfg.bytes_gc4;
     off = (off + 127) & ~127;
     cfg.off_slab = off; off += im.n_mg * 7 * tile * 4;
     cfg.off_qs = off; off += im.n_sub * tile * 4;

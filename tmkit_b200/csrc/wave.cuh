@@ -1,0 +1,259 @@
+/* wave.cuh - the state-validity pipeline for LARGE scenes, wavefront style (BASELINE.json configs[4]: two arms,
+ * 20 moving geometries, hundreds of static obstacles in a uniform grid).
+ *
+ * The tile kernel (pipeline.cuh) keeps every pose of a state in shared memory so that nothing touches HBM; with 20
+ * moving geometries that slab is 143 KB per 256 states - one CTA of 8 warps per SM - and the lane-divergent grid
+ * walk then runs with nothing to hide its latency behind (measured: 12.5 % of peak warps, issue slots 24 % busy,
+ * 6.8 ms per 2^20 configurations).  For such scenes the arithmetic per state (~15 k instructions) dwarfs the bytes
+ * of its poses (560 B), so here the phases are separate kernels that hand their data through HBM / L2 and each
+ * runs at full occupancy:
+ *
+ *   k_wave_fk      one thread = one state: the joint chain in registers, every moving geometry's pose written to
+ *                  planes [geom * 7 + k][state] (coalesced), hit flag cleared
+ *   k_wave_broad   one thread = one (state, moving geometry); blockIdx.y is the geometry, so the partner lists are
+ *                  CTA-uniform (broadcast loads) and only the grid walk diverges; the grid's walk arrays sit in
+ *                  shared memory; survivors are staged per warp in shared memory and flushed with one atomic
+ *   k_wave_quick   one thread = one surviving (state, pair): quick certificates (dev_math.cuh quick_pair); HIT sets
+ *                  the state's flag, undecided pairs go to a (state, pair) list, FP32-ambiguous ones to the exact
+ *                  re-check list
+ *   k_wave_export  one thread = one undecided pair of a state that is still not known to collide: the record the
+ *                  deferred narrowphase kernels of pipeline.cuh consume (k_conv_items, k_mesh_traverse, ...)
+ *   k_wave_bits    one thread = one state: the validity words
+ *
+ * Verdicts are those of the tile kernel bit for bit: the same tests in the same arithmetic decide every pair.
+ * No reference counterpart exists (the reference checks one state at a time on the CPU).
+ */
+#pragma once
+#include "pipeline.cuh"
+
+namespace tmk {
+
+struct WaveBuf {
+    float *pose;        /* [(geom * 7 + k) * cap + state]: x y z w of the rotation, then the translation */
+    uint8_t *hit;       /* [cap] 1 = the state is known to collide */
+    uint2 *queue;       /* broadphase survivors: (state in the chunk, pair key = ITEM_KEY layout) */
+    uint2 *pend;        /* pairs the quick certificates left open */
+    uint32_t *counters; /* [0] queue fill, [1] pend fill */
+    uint32_t cap;       /* states per chunk */
+    uint32_t queue_cap, pend_cap;
+};
+#define TMK_WAVE_STAGE 224 /* survivors staged per warp before a flush */
+
+__device__ __forceinline__ Xf<float> wave_pose(const WaveBuf &w, int g, uint32_t s) {
+    const float *o = w.pose + (size_t)g * 7 * w.cap + s;
+    Xf<float> X;
+    X.r.x = o[0]; X.r.y = o[w.cap]; X.r.z = o[2 * (size_t)w.cap]; X.r.w = o[3 * (size_t)w.cap];
+    X.v.x = o[4 * (size_t)w.cap]; X.v.y = o[5 * (size_t)w.cap]; X.v.z = o[6 * (size_t)w.cap];
+    return X;
+}
+
+template <class Src>
+__global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveBuf w) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const typename Src::State st = src.prepare(s);
+    if (!st.live) return;
+    w.hit[s] = im.static_hit ? 1 : 0;
+    Xf<float> jp[TMK_MAXJ];
+    for (int j = 0; j < im.n_joint; j++) {
+        const DJoint<float> &J = im.joints[j];
+        Xf<float> par;
+        if (J.parent >= 0) par = jp[J.parent];
+        const Xf<float> cur = fk_joint(xload(J.E), mk<float>(J.ax[0], J.ax[1], J.ax[2]), J.off, J.type,
+                                       src.template load1<float>(st, J.qslot), J.parent >= 0 ? &par : (const Xf<float> *)nullptr);
+        jp[j] = cur;
+        for (int a = im.jg_begin[j]; a < im.jg_begin[j + 1]; a++) {
+            const Xf<float> XA = xmul(cur, xload(im.mg[a].tf));
+            float *o = w.pose + (size_t)a * 7 * w.cap + s;
+            o[0] = XA.r.x; o[w.cap] = XA.r.y; o[2 * (size_t)w.cap] = XA.r.z; o[3 * (size_t)w.cap] = XA.r.w;
+            o[4 * (size_t)w.cap] = XA.v.x; o[5 * (size_t)w.cap] = XA.v.y; o[6 * (size_t)w.cap] = XA.v.z;
+        }
+    }
+}
+
+/* broadphase of moving geometry a = blockIdx.y against its partner lists and the static grid */
+__global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, uint32_t n, UncList unc, size_t id_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t cnt[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const StaticGrid &G = im.grid;
+    /* shared memory: [stage: 8 warps x TMK_WAVE_STAGE uint2][cell starts][item spheres][item ids] */
+    uint2 *stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE;
+    const int n_cell = G.on ? G.nx * G.ny * G.nz + 1 : 0;
+    int *gcell = (int *)(smem + sizeof(uint2) * 8 * TMK_WAVE_STAGE);
+    float4 *gc4 = (float4 *)(gcell + ((n_cell + 3) & ~3));
+    unsigned short *gitems = (unsigned short *)(gc4 + (G.on ? G.n_items : 0));
+    if (G.on) {
+        for (int i = tid; i < n_cell; i += 256) gcell[i] = G.cell_start[i];
+        for (int i = tid; i < G.n_items; i += 256) { gc4[i] = G.c4[i]; gitems[i] = G.items[i]; }
+    }
+    if (lane == 0) cnt[warp] = 0;
+    __syncthreads();
+
+    const int a = blockIdx.y;
+    const uint32_t s = blockIdx.x * 256u + tid;
+    const bool live = s < n && w.hit[s] == 0;
+    const DGeom<float> &A = im.mg[a];
+    const uint32_t sc = s < n ? s : 0;
+    const size_t cap = w.cap;
+    const float *oa = w.pose + (size_t)a * 7 * cap + sc;
+    Vec3<float> ca = mk<float>(oa[4 * cap], oa[5 * cap], oa[6 * cap]);
+    if (A.shape == K_MESH) ca = bound_centre(A, wave_pose(w, a, sc));
+    const float ra = A.brad + Num<float>::eps() * 4.0f;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t *PAIRS = im.t_pairs;
+    const float4 *PS4 = (const float4 *)im.ps4;
+    const SQuick *SQ = (const SQuick *)im.sq;
+    const int *PA = im.pa_begin;
+
+    auto put = [&](uint32_t idx, int b, int b_static) {
+        const uint2 item = make_uint2(s, ITEM_KEY(item_pack(0, a, b, b_static)));
+        if (idx < TMK_WAVE_STAGE) stage[idx] = item;
+        else { /* the warp's staging area is full: straight to the queue */
+            const uint32_t k = atomicAdd(&w.counters[0], 1u);
+            if (k < w.queue_cap) w.queue[k] = item;
+            else *unc.overflow = 1u;
+        }
+    };
+    auto enqueue = [&](int p, bool pass) { /* warp-uniform call */
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cnt[warp], (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                const uint32_t wd = PAIRS[p];
+                put(base + __popc(m & lt_mask), (int)((wd >> 8) & 0xffff), (int)((wd >> 24) & 1));
+            }
+        }
+    };
+    int p = PA[3 * a];
+    const int e0 = PA[3 * a + 1], e1 = PA[3 * a + 2], e2 = PA[3 * a + 3];
+    for (; p < e0; p++) { /* static partners by bounding sphere */
+        const float4 c4 = PS4[p];
+        const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+        const float reach = ra + c4.w;
+        enqueue(p, live && dx * dx + dy * dy + dz * dz <= reach * reach);
+    }
+    for (; p < e1; p++) { /* static boxes / mesh boxes: bounding sphere of A against the box itself */
+        const int b = (PAIRS[p] >> 8) & 0xffff;
+        const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
+        const float4 x4 = *reinterpret_cast<const float4 *>(&SQ[b].a0x);
+        const float4 y4 = *reinterpret_cast<const float4 *>(&SQ[b].a1x);
+        const float4 z4 = *reinterpret_cast<const float4 *>(&SQ[b].a2x);
+        const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+        const float ex = fmaxf(fabsf(dx * x4.x + dy * x4.y + dz * x4.z) - x4.w, 0.f);
+        const float ey = fmaxf(fabsf(dx * y4.x + dy * y4.y + dz * y4.z) - y4.w, 0.f);
+        const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
+        enqueue(p, live && ex * ex + ey * ey + ez * ez <= ra * ra);
+    }
+    for (; p < e2; p++) { /* moving partners */
+        const int b = (PAIRS[p] >> 8) & 0xffff;
+        const DGeom<float> &B = im.mg[b];
+        const float *ob = w.pose + (size_t)b * 7 * cap + sc;
+        Vec3<float> cb = mk<float>(ob[4 * cap], ob[5 * cap], ob[6 * cap]);
+        if (B.shape == K_MESH) cb = bound_centre(B, wave_pose(w, b, sc));
+        const Vec3<float> d = cb - ca;
+        const float reach = ra + B.brad;
+        enqueue(p, live && dot(d, d) <= reach * reach);
+    }
+    if (G.on && live) { /* the grid cells the bounding sphere can reach (lane-divergent) */
+        const float rq = ra + G.r_max;
+        const int x0 = max(0, (int)floorf((ca.x - rq - G.ox) * G.inv_h)), x1 = min(G.nx - 1, (int)floorf((ca.x + rq - G.ox) * G.inv_h));
+        const int y0 = max(0, (int)floorf((ca.y - rq - G.oy) * G.inv_h)), y1 = min(G.ny - 1, (int)floorf((ca.y + rq - G.oy) * G.inv_h));
+        const int z0 = max(0, (int)floorf((ca.z - rq - G.oz) * G.inv_h)), z1 = min(G.nz - 1, (int)floorf((ca.z + rq - G.oz) * G.inv_h));
+        const uint32_t *live_row = G.live + (size_t)a * G.wps;
+        for (int z = z0; z <= z1; z++)
+            for (int y = y0; y <= y1; y++) {
+                const int row = (z * G.ny + y) * G.nx;
+                const int k1 = gcell[row + x1 + 1];
+                for (int k = gcell[row + x0]; k < k1; k++) {
+                    const float4 c4 = gc4[k];
+                    const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+                    const float reach = ra + c4.w;
+                    if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
+                    const int b = gitems[k];
+                    if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
+                    put(atomicAdd(&cnt[warp], 1u), b, 1);
+                }
+            }
+    }
+    __syncwarp();
+    /* flush the warp's staged survivors with one atomic */
+    const uint32_t nst = min(cnt[warp], (uint32_t)TMK_WAVE_STAGE);
+    if (nst) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&w.counters[0], nst);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < nst; i += 32) {
+            if (base + i < w.queue_cap) w.queue[base + i] = stage[i];
+            else *unc.overflow = 1u;
+        }
+    }
+    (void)id_base;
+}
+
+/* quick certificates for the broadphase survivors */
+__global__ void __launch_bounds__(256) k_wave_quick(Image<float> im, WaveBuf w, UncList unc, size_t id_base) {
+    uint32_t n = w.counters[0];
+    if (n > w.queue_cap) n = w.queue_cap;
+    const SQuick *SQ = (const SQuick *)im.sq;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 it = w.queue[i];
+        const uint32_t s = it.x, key = it.y;
+        if (w.hit[s]) continue;
+        const int a = ITEM_A(key), b = ITEM_B(key);
+        const DGeom<float> &A = im.mg[a];
+        const int shape_b = ITEM_STATIC(key) ? im.sg[b].shape : im.mg[b].shape;
+        int r = NEED;
+        if (A.shape != K_MESH && shape_b != K_MESH) {
+            const QG qa = qg_from_pose(A, wave_pose(w, a, s));
+            if (ITEM_STATIC(key)) r = quick_pair(A.shape, qa, shape_b, qg_from_static(SQ[b]));
+            else r = quick_pair(A.shape, qa, shape_b, qg_from_pose(im.mg[b], wave_pose(w, b, s)));
+        }
+        if (r == HIT) w.hit[s] = 1;
+        else if (r == UNC) unc_emit(unc, (uint32_t)(id_base + s), 0u, key, TMK_WHOLE_PAIR);
+        else if (r == NEED) {
+            const uint32_t k = atomicAdd(&w.counters[1], 1u);
+            if (k < w.pend_cap) w.pend[k] = it;
+            else unc_emit(unc, (uint32_t)(id_base + s), 0u, key, TMK_WHOLE_PAIR);
+        }
+    }
+}
+
+/* records for the deferred narrowphase, only for states no certificate has condemned yet */
+__global__ void __launch_bounds__(256) k_wave_export(Image<float> im, WaveBuf w, UncList unc, size_t id_base) {
+    uint32_t n = w.counters[1];
+    if (n > w.pend_cap) n = w.pend_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 it = w.pend[i];
+        const uint32_t s = it.x, key = it.y;
+        if (w.hit[s]) continue;
+        const int a = ITEM_A(key), b = ITEM_B(key);
+        const int shape_b = ITEM_STATIC(key) ? im.sg[b].shape : im.mg[b].shape;
+        const bool mesh = im.mg[a].shape == K_MESH || shape_b == K_MESH;
+        const uint32_t dst = atomicAdd(mesh ? unc.mesh_n : unc.conv_n, 1u);
+        if (dst >= (mesh ? unc.mesh_cap : unc.conv_cap)) {
+            unc_emit(unc, (uint32_t)(id_base + s), 0u, key, TMK_WHOLE_PAIR); /* list full: decide it exactly */
+            continue;
+        }
+        const Xf<float> XA = wave_pose(w, a, s);
+        Xf<float> XB = XA;
+        if (!ITEM_STATIC(key)) XB = wave_pose(w, b, s);
+        float4 *rec = (mesh ? unc.mesh_items : unc.conv_items) + (size_t)dst * TMK_MESH_REC;
+        rec[0] = make_float4(__uint_as_float((uint32_t)(id_base + s)), __uint_as_float(0u), __uint_as_float(key), 0.f);
+        rec[1] = make_float4(XA.r.x, XA.r.y, XA.r.z, XA.r.w);
+        rec[2] = make_float4(XA.v.x, XA.v.y, XA.v.z, XB.v.x);
+        rec[3] = make_float4(XB.r.x, XB.r.y, XB.r.z, XB.r.w);
+        rec[4] = make_float4(XB.v.y, XB.v.z, 0.f, 0.f);
+    }
+}
+
+/* validity words of the chunk: bit = no certificate says the state collides (the deferred kernels clear more) */
+__global__ void __launch_bounds__(256) k_wave_bits(WaveBuf w, uint32_t n, uint32_t *bits_chunk) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < n && w.hit[s] == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && s < n) bits_chunk[s >> 5] = m;
+}
+
+} /* namespace tmk */
