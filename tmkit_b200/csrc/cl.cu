@@ -5,6 +5,7 @@
  * .cu only because it launches kernels.  No CPU fallback: every compute entry point needs a
  * CUDA device and aborts loudly without one.
  */
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -378,7 +379,7 @@ extern "C" void tmk_mesh_compiled_release(void *compiled) { delete (HostMesh *)c
 
 /* ------------------------------------------------------------------ the collision context */
 struct ImageDev {
-    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, g_cells, g_items, g_live, g_c4;
+    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, g_cells, g_items, g_live, g_c4, g_rstart, g_rc, g_rid;
     Image<float> f;
     Image<double> d;
     std::vector<uint32_t> h_pairs;
@@ -577,7 +578,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
                     &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_conv, &cl->d_tri, &cl->d_wpose, &cl->d_whit, &cl->d_wqueue, &cl->d_wpend, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
                     &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4, &cl->img.tpairs, &cl->img.g_cells, &cl->img.g_items,
-                    &cl->img.g_live, &cl->img.g_c4};
+                    &cl->img.g_live, &cl->img.g_c4, &cl->img.g_rstart, &cl->img.g_rc, &cl->img.g_rid};
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
     for (auto &g : cl->edge_graphs) cudaGraphExecDestroy(g.exec);
@@ -907,6 +908,92 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
             if (((p.w >> 24) & 1) && gridded[(p.w >> 8) & 0xffff])
                 live_ms[(size_t)p.owner * wps + (((p.w >> 8) & 0xffff) >> 5)] |= 1u << (((p.w >> 8) & 0xffff) & 31);
     }
+    /* reach lists for the wavefront broadphase (kernels.cuh StaticGrid::r_*) */
+    std::vector<int> r_start(2, 0);
+    std::vector<uint2> r_c(1, make_uint2(0, 0));
+    std::vector<unsigned short> r_id(1, 0);
+    if (grid_on) {
+        double ra_max = 0;
+        for (auto &G : mg) ra_max = std::max(ra_max, G.brad * (1 + 1e-6));
+        ra_max += 1e-4; /* the kernel's pad (4 eps) and its float cell arithmetic */
+        double H = getenv("TMK_REACH_H") ? atof(getenv("TMK_REACH_H")) : 0.125; /* tuning aid */
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        std::vector<double> rb(sgv.size(), 0.0);
+        for (size_t b = 0; b < sgv.size(); b++) {
+            if (!gridded[b]) continue;
+            rb[b] = (double)(float)(sgv[b].brad * (1 + 1e-6)) * (1 + 1e-6); /* >= the float radius the quick tables hold */
+            for (int c = 0; c < 3; c++) {
+                lo[c] = std::min(lo[c], sgv[b].tf[4 + c] - ra_max - rb[b] - 1e-3);
+                hi[c] = std::max(hi[c], sgv[b].tf[4 + c] + ra_max + rb[b] + 1e-3);
+            }
+        }
+        int dims[3];
+        for (;;) {
+            size_t cells = 1;
+            for (int c = 0; c < 3; c++) { dims[c] = std::max(1, (int)ceil((hi[c] - lo[c]) / H)); cells *= (size_t)dims[c]; }
+            if (cells <= (size_t(1) << 20)) break;
+            H *= 1.26; /* halve the cell count */
+        }
+        const size_t n_cell = (size_t)dims[0] * dims[1] * dims[2];
+        /* quantisation: coordinates relative to the cell centre are below R + h sqrt(3)/2 in magnitude */
+        double vmax = 0;
+        for (size_t b = 0; b < sgv.size(); b++)
+            if (gridded[b]) vmax = std::max(vmax, ra_max + rb[b] + H);
+        const double ulp = ldexp(1.0, (int)floor(log2(std::max(vmax, 1e-3))) - 10); /* half precision: 10 mantissa bits */
+        const double q_err = 0.5 * ulp * sqrt(3.0) + 1e-6;
+        auto half_up = [](double v) { /* smallest half >= v (v > 0) */
+            __half h = __float2half_rn((float)v);
+            unsigned short u = __half_as_ushort(h);
+            if ((double)__half2float(h) < v) u++;
+            return u;
+        };
+        auto half_rn = [](double v) { return (unsigned short)__half_as_ushort(__float2half_rn((float)v)); };
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<int> fill;
+            if (pass == 0) r_start.assign(n_cell + 1, 0);
+            else {
+                for (size_t k = 0; k < n_cell; k++) r_start[k + 1] += r_start[k];
+                r_c.assign((size_t)r_start[n_cell] + 1, make_uint2(0, 0));
+                r_id.assign((size_t)r_start[n_cell] + 1, 0);
+                fill.assign(r_start.begin(), r_start.end() - 1);
+            }
+            for (size_t b = 0; b < sgv.size(); b++) {
+                if (!gridded[b]) continue;
+                const double R = ra_max + rb[b] + 1e-4, *c = &sgv[b].tf[4];
+                int i0[3], i1[3];
+                for (int a = 0; a < 3; a++) {
+                    i0[a] = std::max(0, (int)floor((c[a] - R - lo[a]) / H));
+                    i1[a] = std::min(dims[a] - 1, (int)floor((c[a] + R - lo[a]) / H));
+                }
+                for (int z = i0[2]; z <= i1[2]; z++)
+                    for (int y = i0[1]; y <= i1[1]; y++)
+                        for (int x = i0[0]; x <= i1[0]; x++) {
+                            const int ix[3] = {x, y, z};
+                            double d2 = 0, rel[3];
+                            for (int a = 0; a < 3; a++) {
+                                const double bl = lo[a] + ix[a] * H, bh = bl + H;
+                                const double e = std::max(std::max(bl - c[a], c[a] - bh), 0.0);
+                                d2 += e * e;
+                                rel[a] = c[a] - (bl + 0.5 * H);
+                            }
+                            if (d2 > R * R) continue;
+                            const size_t cell = ((size_t)z * dims[1] + y) * dims[0] + x;
+                            if (pass == 0) { r_start[cell + 1]++; continue; }
+                            const int k = fill[cell]++;
+                            r_c[k] = make_uint2((uint32_t)half_rn(rel[0]) | ((uint32_t)half_rn(rel[1]) << 16),
+                                                (uint32_t)half_rn(rel[2]) | ((uint32_t)half_up(rb[b] + q_err) << 16));
+                            r_id[k] = (unsigned short)b;
+                        }
+            }
+        }
+        grid.r_on = 1;
+        grid.r_nx = dims[0]; grid.r_ny = dims[1]; grid.r_nz = dims[2];
+        grid.r_ox = (float)lo[0]; grid.r_oy = (float)lo[1]; grid.r_oz = (float)lo[2];
+        grid.r_h = (float)H; grid.r_inv_h = (float)(1.0 / H);
+        if (getenv("TMK_DEBUG_IMAGE"))
+            fprintf(stderr, "tmkcl reach lists: %d x %d x %d cells of %.3f m, %d entries (%.1f per cell), query radius <= %.3f m\n", dims[0], dims[1],
+                    dims[2], H, r_start[n_cell], (double)r_start[n_cell] / (double)n_cell, ra_max);
+    }
     std::vector<P> tpairs;
     for (auto &p : pairs)
         if (!(((p.w >> 24) & 1) && gridded[(p.w >> 8) & 0xffff])) tpairs.push_back(p);
@@ -1025,6 +1112,13 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     grid.cell_start = (const int *)im.g_cells.p;
     grid.items = (const unsigned short *)im.g_items.p;
     grid.live = (const uint32_t *)im.g_live.p;
+    upload(im.g_rstart, r_start, cl->stream);
+    upload(im.g_rc, r_c, cl->stream);
+    upload(im.g_rid, r_id, cl->stream);
+    CK(cudaStreamSynchronize(cl->stream));
+    grid.r_start = (const int *)im.g_rstart.p;
+    grid.r_c = (const uint2 *)im.g_rc.p;
+    grid.r_id = (const unsigned short *)im.g_rid.p;
     grid.c4 = (const float4 *)im.g_c4.p;
     grid.n_items = grid.on ? (int)n_gridded : 0;
     im.d.grid = im.f.grid = grid;
@@ -1166,12 +1260,7 @@ static size_t launch_wave(struct aa_rx_cl *cl, const void *dQ, int layout, size_
     ImageDev &im = cl->img;
     WaveBuf w = wave_buffers(cl, end - begin);
     w.counters = u.n + 16;
-    const StaticGrid &G = im.f.grid;
-    const size_t n_cell = (size_t)G.nx * G.ny * G.nz + 1;
-    const size_t smem = sizeof(uint2) * 8 * TMK_WAVE_STAGE + sizeof(int) * ((n_cell + 3) & ~(size_t)3) + (size_t)G.n_items * 18 + 64;
-    if (smem > 160 * 1024) tmk_die("batch: the static grid (%zu cells, %d items) does not fit the broadphase kernel's shared memory", n_cell, G.n_items);
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_wave_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    const size_t smem = sizeof(uint2) * 8 * TMK_WAVE_STAGE;
     size_t launches = 0;
     for (size_t c0 = begin; c0 < end; c0 += TMK_WAVE_CHUNK) {
         const size_t c1 = std::min(end, c0 + TMK_WAVE_CHUNK);

@@ -58,6 +58,15 @@ struct StaticGrid {
     const float4 *c4;              /* bounding centre + radius of items[k], in the same (cell) order: the walk reads
                                     * this array front to back and touches nothing else until a sphere test passes */
     int n_items;
+    /* reach lists (wave.cuh): a finer grid whose cell lists hold EVERY item a moving geometry centred anywhere in the
+     * cell could touch (items within the largest moving bounding radius + their own of the cell's box), as
+     * (centre relative to the cell centre, radius) in half precision, rounded conservatively: one contiguous
+     * run per query instead of a walk over dozens of nearly empty cells */
+    int r_on, r_nx, r_ny, r_nz;
+    float r_ox, r_oy, r_oz, r_h, r_inv_h;
+    const int *r_start;            /* [r_nx*r_ny*r_nz + 1] */
+    const uint2 *r_c;              /* half2(dx, dy), half2(dz, radius) */
+    const unsigned short *r_id;    /* static geometry index of every entry */
     const uint32_t *live;          /* [n_mg][wps] bit b: pair (a, static b) is a candidate (not allowed-away, reachable) */
     int wps;
 };

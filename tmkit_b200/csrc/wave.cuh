@@ -11,8 +11,10 @@
  *   k_wave_fk      one thread = one state: the joint chain in registers, every moving geometry's pose written to
  *                  planes [geom * 7 + k][state] (coalesced), hit flag cleared
  *   k_wave_broad   one thread = one (state, moving geometry); blockIdx.y is the geometry, so the partner lists are
- *                  CTA-uniform (broadcast loads) and only the grid walk diverges; the grid's walk arrays sit in
- *                  shared memory; survivors are staged per warp in shared memory and flushed with one atomic
+ *                  CTA-uniform (broadcast loads); the small obstacles come from the reach list of the one grid cell
+ *                  the geometry's centre lies in (a contiguous run of half-precision spheres, rounded
+ *                  conservatively, read through L2); survivors are staged per warp in shared memory and flushed
+ *                  with one atomic
  *   k_wave_quick   one thread = one surviving (state, pair): quick certificates (dev_math.cuh quick_pair); HIT sets
  *                  the state's flag, undecided pairs go to a (state, pair) list, FP32-ambiguous ones to the exact
  *                  re-check list
@@ -24,6 +26,8 @@
  * No reference counterpart exists (the reference checks one state at a time on the CPU).
  */
 #pragma once
+#include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include "pipeline.cuh"
 
 namespace tmk {
@@ -76,16 +80,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     __shared__ uint32_t cnt[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StaticGrid &G = im.grid;
-    /* shared memory: [stage: 8 warps x TMK_WAVE_STAGE uint2][cell starts][item spheres][item ids] */
-    uint2 *stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE;
-    const int n_cell = G.on ? G.nx * G.ny * G.nz + 1 : 0;
-    int *gcell = (int *)(smem + sizeof(uint2) * 8 * TMK_WAVE_STAGE);
-    float4 *gc4 = (float4 *)(gcell + ((n_cell + 3) & ~3));
-    unsigned short *gitems = (unsigned short *)(gc4 + (G.on ? G.n_items : 0));
-    if (G.on) {
-        for (int i = tid; i < n_cell; i += 256) gcell[i] = G.cell_start[i];
-        for (int i = tid; i < G.n_items; i += 256) { gc4[i] = G.c4[i]; gitems[i] = G.items[i]; }
-    }
+    uint2 *stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE; /* 8 warps x TMK_WAVE_STAGE survivors */
     if (lane == 0) cnt[warp] = 0;
     __syncthreads();
 
@@ -156,26 +151,28 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
         const float reach = ra + B.brad;
         enqueue(p, live && dot(d, d) <= reach * reach);
     }
-    if (G.on && live) { /* the grid cells the bounding sphere can reach (lane-divergent) */
-        const float rq = ra + G.r_max;
-        const int x0 = max(0, (int)floorf((ca.x - rq - G.ox) * G.inv_h)), x1 = min(G.nx - 1, (int)floorf((ca.x + rq - G.ox) * G.inv_h));
-        const int y0 = max(0, (int)floorf((ca.y - rq - G.oy) * G.inv_h)), y1 = min(G.ny - 1, (int)floorf((ca.y + rq - G.oy) * G.inv_h));
-        const int z0 = max(0, (int)floorf((ca.z - rq - G.oz) * G.inv_h)), z1 = min(G.nz - 1, (int)floorf((ca.z + rq - G.oz) * G.inv_h));
-        const uint32_t *live_row = G.live + (size_t)a * G.wps;
-        for (int z = z0; z <= z1; z++)
-            for (int y = y0; y <= y1; y++) {
-                const int row = (z * G.ny + y) * G.nx;
-                const int k1 = gcell[row + x1 + 1];
-                for (int k = gcell[row + x0]; k < k1; k++) {
-                    const float4 c4 = gc4[k];
-                    const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-                    const float reach = ra + c4.w;
-                    if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
-                    const int b = gitems[k];
-                    if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
-                    put(atomicAdd(&cnt[warp], 1u), b, 1);
-                }
+    if (G.r_on && live) { /* one run of candidates: everything a geometry centred in this cell could touch */
+        const float fx = (ca.x - G.r_ox) * G.r_inv_h, fy = (ca.y - G.r_oy) * G.r_inv_h, fz = (ca.z - G.r_oz) * G.r_inv_h;
+        const int ix = (int)floorf(fx), iy = (int)floorf(fy), iz = (int)floorf(fz);
+        if (ix >= 0 && iy >= 0 && iz >= 0 && ix < G.r_nx && iy < G.r_ny && iz < G.r_nz) {
+            const int cell = (iz * G.r_ny + iy) * G.r_nx + ix;
+            /* the query centre relative to the cell centre, like the entries */
+            const float qx = ca.x - (G.r_ox + ((float)ix + 0.5f) * G.r_h), qy = ca.y - (G.r_oy + ((float)iy + 0.5f) * G.r_h),
+                        qz = ca.z - (G.r_oz + ((float)iz + 0.5f) * G.r_h);
+            const uint32_t *live_row = G.live + (size_t)a * G.wps;
+            const int k1 = G.r_start[cell + 1];
+            for (int k = G.r_start[cell]; k < k1; k++) {
+                const uint2 e = G.r_c[k];
+                const float2 xy = __half22float2(*reinterpret_cast<const __half2 *>(&e.x));
+                const float2 zr = __half22float2(*reinterpret_cast<const __half2 *>(&e.y));
+                const float dx = xy.x - qx, dy = xy.y - qy, dz = zr.x - qz;
+                const float reach = ra + zr.y;
+                if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
+                const int b = G.r_id[k]; /* rare from here on */
+                if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
+                put(atomicAdd(&cnt[warp], 1u), b, 1);
             }
+        }
     }
     __syncwarp();
     /* flush the warp's staged survivors with one atomic */
@@ -213,7 +210,10 @@ __global__ void __launch_bounds__(256) k_wave_quick(Image<float> im, WaveBuf w, 
         if (r == HIT) w.hit[s] = 1;
         else if (r == UNC) unc_emit(unc, (uint32_t)(id_base + s), 0u, key, TMK_WHOLE_PAIR);
         else if (r == NEED) {
-            const uint32_t k = atomicAdd(&w.counters[1], 1u);
+            const auto g = cooperative_groups::coalesced_threads(); /* one atomic per warp, not per item */
+            uint32_t k = 0;
+            if (g.thread_rank() == 0) k = atomicAdd(&w.counters[1], (uint32_t)g.size());
+            k = g.shfl(k, 0) + g.thread_rank();
             if (k < w.pend_cap) w.pend[k] = it;
             else unc_emit(unc, (uint32_t)(id_base + s), 0u, key, TMK_WHOLE_PAIR);
         }
@@ -231,7 +231,16 @@ __global__ void __launch_bounds__(256) k_wave_export(Image<float> im, WaveBuf w,
         const int a = ITEM_A(key), b = ITEM_B(key);
         const int shape_b = ITEM_STATIC(key) ? im.sg[b].shape : im.mg[b].shape;
         const bool mesh = im.mg[a].shape == K_MESH || shape_b == K_MESH;
-        const uint32_t dst = atomicAdd(mesh ? unc.mesh_n : unc.conv_n, 1u);
+        uint32_t dst = 0;
+        if (mesh) {
+            const auto g = cooperative_groups::coalesced_threads();
+            if (g.thread_rank() == 0) dst = atomicAdd(unc.mesh_n, (uint32_t)g.size());
+            dst = g.shfl(dst, 0) + g.thread_rank();
+        } else {
+            const auto g = cooperative_groups::coalesced_threads();
+            if (g.thread_rank() == 0) dst = atomicAdd(unc.conv_n, (uint32_t)g.size());
+            dst = g.shfl(dst, 0) + g.thread_rank();
+        }
         if (dst >= (mesh ? unc.mesh_cap : unc.conv_cap)) {
             unc_emit(unc, (uint32_t)(id_base + s), 0u, key, TMK_WHOLE_PAIR); /* list full: decide it exactly */
             continue;
