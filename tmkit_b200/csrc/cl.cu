@@ -1269,7 +1269,7 @@ static size_t launch_wave(struct aa_rx_cl *cl, const void *dQ, int layout, size_
         src.p = dQ; src.layout = layout; src.ld = ld; src.n = n; src.s_begin = c0;
         CK(cudaMemsetAsync(w.counters, 0, 8, s));
         const unsigned gx = (n + 255) / 256;
-        k_wave_fk<SrcConfigs><<<gx, 256, 0, s>>>(im.f, src, w);
+        k_wave_fk<SrcConfigs><<<gx, 256, smem, s>>>(im.f, src, w, u);
         k_wave_broad<<<dim3(gx, (unsigned)im.f.n_mg), 256, smem, s>>>(im.f, w, n, u, c0);
         k_wave_quick<<<148 * 8, 256, 0, s>>>(im.f, w, u, c0);
         k_wave_export<<<148 * 4, 256, 0, s>>>(im.f, w, u, c0);

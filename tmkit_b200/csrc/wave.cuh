@@ -51,27 +51,92 @@ __device__ __forceinline__ Xf<float> wave_pose(const WaveBuf &w, int g, uint32_t
     return X;
 }
 
+/* warp-level staging of broadphase survivors: appended in shared memory, flushed to the queue with one atomic */
+struct WaveStage {
+    uint2 *stage;      /* this warp's TMK_WAVE_STAGE slots */
+    uint32_t *cnt;     /* this warp's fill */
+    __device__ __forceinline__ void put(const WaveBuf &w, const UncList &unc, uint32_t idx, uint32_t s, int a, int b, int b_static) const {
+        const uint2 item = make_uint2(s, ITEM_KEY(item_pack(0, a, b, b_static)));
+        if (idx < TMK_WAVE_STAGE) stage[idx] = item;
+        else { /* the warp's staging area is full: straight to the queue */
+            const uint32_t k = atomicAdd(&w.counters[0], 1u);
+            if (k < w.queue_cap) w.queue[k] = item;
+            else *unc.overflow = 1u;
+        }
+    }
+    /* warp-uniform call: every lane votes, passing lanes get consecutive slots */
+    __device__ __forceinline__ void vote(const WaveBuf &w, const UncList &unc, bool pass, uint32_t s, int a, int b, int b_static, int lane) const {
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cnt, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) put(w, unc, base + __popc(m & ((1u << lane) - 1u)), s, a, b, b_static);
+        }
+    }
+    __device__ __forceinline__ void flush(const WaveBuf &w, const UncList &unc, int lane) const {
+        __syncwarp();
+        const uint32_t nst = min(*cnt, (uint32_t)TMK_WAVE_STAGE);
+        if (nst) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&w.counters[0], nst);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t i = lane; i < nst; i += 32) {
+                if (base + i < w.queue_cap) w.queue[base + i] = stage[i];
+                else *unc.overflow = 1u;
+            }
+        }
+    }
+};
+
+/* FK of every state + the broadphase of the MOVING partners: when a geometry's pose exists the centres of the
+ * moving geometries before it are still in the thread's hands (a pair of two moving geometries is owned by the
+ * later one), so those pairs are voted on here instead of re-reading partner centres from HBM per pair */
 template <class Src>
-__global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveBuf w) {
+__global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveBuf w, UncList unc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t cnt[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WaveStage ws;
+    ws.stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE;
+    ws.cnt = &cnt[warp];
+    if (lane == 0) cnt[warp] = 0;
+    __syncwarp();
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const typename Src::State st = src.prepare(s);
-    if (!st.live) return;
-    w.hit[s] = im.static_hit ? 1 : 0;
+    const bool live = st.live && !im.static_hit;
+    if (st.live) w.hit[s] = im.static_hit ? 1 : 0;
+    const float pad = Num<float>::eps() * 4.0f;
     Xf<float> jp[TMK_MAXJ];
+    float gx[TMK_MAXMG], gy[TMK_MAXMG], gz[TMK_MAXMG];
     for (int j = 0; j < im.n_joint; j++) {
         const DJoint<float> &J = im.joints[j];
         Xf<float> par;
         if (J.parent >= 0) par = jp[J.parent];
-        const Xf<float> cur = fk_joint(xload(J.E), mk<float>(J.ax[0], J.ax[1], J.ax[2]), J.off, J.type,
-                                       src.template load1<float>(st, J.qslot), J.parent >= 0 ? &par : (const Xf<float> *)nullptr);
+        const float qv = st.live ? src.template load1<float>(st, J.qslot) : 0.f;
+        const Xf<float> cur = fk_joint(xload(J.E), mk<float>(J.ax[0], J.ax[1], J.ax[2]), J.off, J.type, qv,
+                                       J.parent >= 0 ? &par : (const Xf<float> *)nullptr);
         jp[j] = cur;
         for (int a = im.jg_begin[j]; a < im.jg_begin[j + 1]; a++) {
-            const Xf<float> XA = xmul(cur, xload(im.mg[a].tf));
-            float *o = w.pose + (size_t)a * 7 * w.cap + s;
-            o[0] = XA.r.x; o[w.cap] = XA.r.y; o[2 * (size_t)w.cap] = XA.r.z; o[3 * (size_t)w.cap] = XA.r.w;
-            o[4 * (size_t)w.cap] = XA.v.x; o[5 * (size_t)w.cap] = XA.v.y; o[6 * (size_t)w.cap] = XA.v.z;
+            const DGeom<float> &A = im.mg[a];
+            const Xf<float> XA = xmul(cur, xload(A.tf));
+            if (st.live) {
+                float *o = w.pose + (size_t)a * 7 * w.cap + s;
+                o[0] = XA.r.x; o[w.cap] = XA.r.y; o[2 * (size_t)w.cap] = XA.r.z; o[3 * (size_t)w.cap] = XA.r.w;
+                o[4 * (size_t)w.cap] = XA.v.x; o[5 * (size_t)w.cap] = XA.v.y; o[6 * (size_t)w.cap] = XA.v.z;
+            }
+            const Vec3<float> ca = bound_centre(A, XA);
+            gx[a] = ca.x; gy[a] = ca.y; gz[a] = ca.z;
+            const float ra = A.brad + pad;
+            for (int p = im.pa_begin[3 * a + 2]; p < im.pa_begin[3 * a + 3]; p++) { /* moving partners */
+                const int b = (im.t_pairs[p] >> 8) & 0xffff;
+                const float dx = gx[b] - ca.x, dy = gy[b] - ca.y, dz = gz[b] - ca.z;
+                const float reach = ra + im.mg[b].brad;
+                ws.vote(w, unc, live && dx * dx + dy * dy + dz * dz <= reach * reach, s, a, b, 0, lane);
+            }
         }
     }
+    ws.flush(w, unc, lane);
 }
 
 /* broadphase of moving geometry a = blockIdx.y against its partner lists and the static grid */
@@ -94,32 +159,17 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     Vec3<float> ca = mk<float>(oa[4 * cap], oa[5 * cap], oa[6 * cap]);
     if (A.shape == K_MESH) ca = bound_centre(A, wave_pose(w, a, sc));
     const float ra = A.brad + Num<float>::eps() * 4.0f;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t *PAIRS = im.t_pairs;
     const float4 *PS4 = (const float4 *)im.ps4;
     const SQuick *SQ = (const SQuick *)im.sq;
     const int *PA = im.pa_begin;
 
-    auto put = [&](uint32_t idx, int b, int b_static) {
-        const uint2 item = make_uint2(s, ITEM_KEY(item_pack(0, a, b, b_static)));
-        if (idx < TMK_WAVE_STAGE) stage[idx] = item;
-        else { /* the warp's staging area is full: straight to the queue */
-            const uint32_t k = atomicAdd(&w.counters[0], 1u);
-            if (k < w.queue_cap) w.queue[k] = item;
-            else *unc.overflow = 1u;
-        }
-    };
+    WaveStage ws;
+    ws.stage = stage;
+    ws.cnt = &cnt[warp];
     auto enqueue = [&](int p, bool pass) { /* warp-uniform call */
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&cnt[warp], (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) {
-                const uint32_t wd = PAIRS[p];
-                put(base + __popc(m & lt_mask), (int)((wd >> 8) & 0xffff), (int)((wd >> 24) & 1));
-            }
-        }
+        const uint32_t wd = PAIRS[p];
+        ws.vote(w, unc, pass, s, a, (int)((wd >> 8) & 0xffff), (int)((wd >> 24) & 1), lane);
     };
     int p = PA[3 * a];
     const int e0 = PA[3 * a + 1], e1 = PA[3 * a + 2], e2 = PA[3 * a + 3];
@@ -141,16 +191,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
         const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
         enqueue(p, live && ex * ex + ey * ey + ez * ez <= ra * ra);
     }
-    for (; p < e2; p++) { /* moving partners */
-        const int b = (PAIRS[p] >> 8) & 0xffff;
-        const DGeom<float> &B = im.mg[b];
-        const float *ob = w.pose + (size_t)b * 7 * cap + sc;
-        Vec3<float> cb = mk<float>(ob[4 * cap], ob[5 * cap], ob[6 * cap]);
-        if (B.shape == K_MESH) cb = bound_centre(B, wave_pose(w, b, sc));
-        const Vec3<float> d = cb - ca;
-        const float reach = ra + B.brad;
-        enqueue(p, live && dot(d, d) <= reach * reach);
-    }
+    (void)e2; /* the moving partners were voted on by k_wave_fk */
     if (G.r_on && live) { /* one run of candidates: everything a geometry centred in this cell could touch */
         const float fx = (ca.x - G.r_ox) * G.r_inv_h, fy = (ca.y - G.r_oy) * G.r_inv_h, fz = (ca.z - G.r_oz) * G.r_inv_h;
         const int ix = (int)floorf(fx), iy = (int)floorf(fy), iz = (int)floorf(fz);
@@ -170,22 +211,11 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
                 if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
                 const int b = G.r_id[k]; /* rare from here on */
                 if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
-                put(atomicAdd(&cnt[warp], 1u), b, 1);
+                ws.put(w, unc, atomicAdd(&cnt[warp], 1u), s, a, b, 1);
             }
         }
     }
-    __syncwarp();
-    /* flush the warp's staged survivors with one atomic */
-    const uint32_t nst = min(cnt[warp], (uint32_t)TMK_WAVE_STAGE);
-    if (nst) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&w.counters[0], nst);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (uint32_t i = lane; i < nst; i += 32) {
-            if (base + i < w.queue_cap) w.queue[base + i] = stage[i];
-            else *unc.overflow = 1u;
-        }
-    }
+    ws.flush(w, unc, lane);
     (void)id_base;
 }
 
