@@ -1229,11 +1229,13 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     return u;
 }
 
-/* ---- large scenes: the wavefront pipeline (wave.cuh) instead of the tile kernel ---- */
+/* ---- configuration batches: the wavefront pipeline (wave.cuh) instead of the tile kernel ---- */
 #define TMK_WAVE_CHUNK (size_t(1) << 20)
 static bool wave_wanted(const struct aa_rx_cl *cl, size_t n_states) {
     static const bool off = getenv("TMK_NO_WAVE") != nullptr; /* A/B aid and test hook */
-    return cl->img.f.grid.on && n_states >= 4096 && !off && !getenv("TMK_NO_WAVE_NOW");
+    /* every batch large enough to fill the GPU per kernel; small batches (a planner's frontier) and the swept-edge
+     * levels stay on the tile kernel, which needs one launch and no scratch in HBM */
+    return n_states >= 4096 && cl->img.f.n_mg <= 64 && !off && !getenv("TMK_NO_WAVE_NOW");
 }
 static WaveBuf wave_buffers(struct aa_rx_cl *cl, size_t n_states) {
     WaveBuf w;
