@@ -1230,8 +1230,16 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
 }
 
 /* ---- configuration batches: the wavefront pipeline (wave.cuh) instead of the tile kernel ---- */
-#define TMK_WAVE_CHUNK (size_t(1) << 20)
-static bool wave_wanted(const struct aa_rx_cl *cl, size_t n_states) {
+static size_t wave_chunk() {
+    static const size_t c = getenv("TMK_WAVE_CHUNK") ? (size_t)std::max(4096L, atol(getenv("TMK_WAVE_CHUNK"))) & ~(size_t)31 : (size_t(1) << 20); /* tuning aid */
+    return c;
+}
+#define TMK_WAVE_CHUNK wave_chunk()
+static bool wave_wanted(const struct aa_rx_cl *cl, size_t n_states, bool host_chunk = false) {
+    /* behind the chunk-wise copies of the host-buffer call the tile kernel's single launch per chunk wins on small
+     * scenes (measured 1.47 vs 1.54 ms per 2^20 double rows); large scenes stay with the wavefront kernels, which
+     * are several times faster there, on larger chunks */
+    if (host_chunk && !cl->img.f.grid.on) return false;
     static const bool off = getenv("TMK_NO_WAVE") != nullptr; /* A/B aid and test hook */
     /* every batch large enough to fill the GPU per kernel; small batches (a planner's frontier) and the swept-edge
      * levels stay on the tile kernel, which needs one launch and no scratch in HBM */
@@ -1350,7 +1358,7 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
         unsigned grid = (unsigned)std::min<size_t>((src.n + T - 1) / T, (size_t)im.wcfg.grid);
         cudaEvent_t *ev = chunk_begin == 0 ? (cl->cur_ev = timing_begin(cl, s)) : cl->cur_ev;
         size_t n_main = 1;
-        if (wave_wanted(cl, c_end - chunk_begin)) n_main = launch_wave(cl, dQ, layout, ld, chunk_begin, c_end, d_bits, u, s);
+        if (wave_wanted(cl, c_end - chunk_begin, !whole)) n_main = launch_wave(cl, dQ, layout, ld, chunk_begin, c_end, d_bits, u, s);
         else launch_tile<SrcConfigs, SinkBits>(im.f, im.wcfg, src, sink, u, (unsigned long long *)nullptr, grid, s);
         CK(cudaGetLastError());
         cl->stats.n_launches += n_main;
@@ -1598,7 +1606,9 @@ static void batch_host_begin(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, co
     cl->d_q.need(n_cfg * ldQ * esz + 16);
     cl->d_bits.need(sizeof(uint32_t) * (nw + 1));
     /* chunk = two full waves of the persistent grid (no tail effect inside a chunk) */
-    const size_t wave = (size_t)std::max(1, cl->img.wcfg.grid) * (size_t)std::max(32, cl->img.wcfg.tile);
+    size_t wave = (size_t)std::max(1, cl->img.wcfg.grid) * (size_t)std::max(32, cl->img.wcfg.tile);
+    if (cl->img.f.grid.on) wave = std::max(wave, (size_t)262144); /* wavefront kernels: five launches per chunk */
+    if (const char *e = getenv("TMK_HOST_WAVE")) wave = (size_t)std::max(4096L, atol(e)) & ~(size_t)1023; /* tuning aid */
     const size_t CH = 2 * wave;
     if (n_cfg <= CH + CH / 2 || cl->stats_on || cl->track || !cl->use_tile || cl->img.wcfg.smem <= 0) {
         if (n_cfg) CK(cudaMemcpyAsync(cl->d_q.p, Q, n_cfg * ldQ * esz, cudaMemcpyHostToDevice, cl->stream));

@@ -173,14 +173,30 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     };
     int p = PA[3 * a];
     const int e0 = PA[3 * a + 1], e1 = PA[3 * a + 2], e2 = PA[3 * a + 3];
-    for (; p < e0; p++) { /* static partners by bounding sphere */
+    /* static partners by bounding sphere: four tests, one vote (most groups have no survivor in any lane) */
+    for (; p + 4 <= e0; p += 4) {
+        bool pass[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float4 c4 = PS4[p + u];
+            const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
+            const float reach = ra + c4.w;
+            pass[u] = live && dx * dx + dy * dy + dz * dz <= reach * reach;
+        }
+        if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) enqueue(p + u, pass[u]);
+        }
+    }
+    for (; p < e0; p++) {
         const float4 c4 = PS4[p];
         const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
         const float reach = ra + c4.w;
         enqueue(p, live && dx * dx + dy * dy + dz * dz <= reach * reach);
     }
-    for (; p < e1; p++) { /* static boxes / mesh boxes: bounding sphere of A against the box itself */
-        const int b = (PAIRS[p] >> 8) & 0xffff;
+    /* static boxes / mesh boxes: bounding sphere of A against the box itself (exact point-box distance) */
+    auto box_pass = [&](int pp) {
+        const int b = (PAIRS[pp] >> 8) & 0xffff;
         const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
         const float4 x4 = *reinterpret_cast<const float4 *>(&SQ[b].a0x);
         const float4 y4 = *reinterpret_cast<const float4 *>(&SQ[b].a1x);
@@ -189,8 +205,13 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
         const float ex = fmaxf(fabsf(dx * x4.x + dy * x4.y + dz * x4.z) - x4.w, 0.f);
         const float ey = fmaxf(fabsf(dx * y4.x + dy * y4.y + dz * y4.z) - y4.w, 0.f);
         const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
-        enqueue(p, live && ex * ex + ey * ey + ez * ez <= ra * ra);
+        return live && ex * ex + ey * ey + ez * ez <= ra * ra;
+    };
+    for (; p + 2 <= e1; p += 2) {
+        const bool p0 = box_pass(p), p1 = box_pass(p + 1);
+        if (__any_sync(0xffffffffu, p0 | p1)) { enqueue(p, p0); enqueue(p + 1, p1); }
     }
+    for (; p < e1; p++) enqueue(p, box_pass(p));
     (void)e2; /* the moving partners were voted on by k_wave_fk */
     if (G.r_on && live) { /* one run of candidates: everything a geometry centred in this cell could touch */
         const float fx = (ca.x - G.r_ox) * G.r_inv_h, fy = (ca.y - G.r_oy) * G.r_inv_h, fz = (ca.z - G.r_oz) * G.r_inv_h;
