@@ -13,6 +13,7 @@ ride in the same line under `secondary`, each with its own value / roofline / e2
     blocks   configs[3]  2^20 right-arm configurations, 32-block tabletop, mesh robot       (weak scaling)
     clutter  configs[4]  ONE batch of 2^24 dual-arm configurations vs 512 primitives, split over the N GPUs
                          in 1024-aligned slices (strong scaling: the batch is fixed, N = 1 runs all of it)
+    fk       north_star kernel (1): batched forward kinematics alone, HBM roofline           (rank-local)
     sussman  configs[0]  the motion side of the Baxter Sussman task-motion plan, end to end (rank 0)
 
 `value` is measured with the inputs resident in HBM through the asynchronous device-pointer entry points
@@ -59,7 +60,7 @@ N_CFG = 1 << 20
 N_EDGE = 100_000
 N_CLUTTER = 1 << 24
 CHUNK = 1 << 20  # the strong-scaled batch is generated chunk by chunk so that its content does not depend on N
-SECONDARY = ("edges", "blocks", "clutter", "sussman")
+SECONDARY = ("edges", "blocks", "clutter", "fk", "sussman")
 PARITY_NOTE = ("CPU arm = the builder's restatement of Amino/FCL/OMPL semantics (oracle/); the reference's own "
                "implementation of this path is not in the reference tree: parity with it is unpinned")
 
@@ -318,8 +319,8 @@ def run_reference(args):
     if args.workload == "all":
         sec = {}
         for wl in SECONDARY:
-            if wl == "sussman":
-                continue  # needs the GPU planner to produce the edge log; reported by the own arm's cpu_baseline
+            if wl in ("sussman", "fk"):
+                continue  # sussman needs the GPU planner's edge log (its CPU replay rides in the own arm); fk has no CPU arm
             sec[wl] = reference_line(wl, 3, 1, args.gpus, 12.0)
         line["secondary"] = sec
     line["amino_fcl"] = amino_probe()
@@ -385,6 +386,79 @@ def run_sussman(args, steps=None, cpu_only=False):
         "e2e": {"value": tot, "unit": "s", "h2d_bytes_per_step": int(2 * 8 * 7 * r.counters["edges_checked"]),
                 "d2h_bytes_per_step": int(4 * ((r.counters["edges_checked"] + 31) // 32 + r.counters["edge_calls"])),
                 "call": "aa_rx_mp_set_start / _set_wsgoal / _plan per action", "note": "bytes: edge end points in, validity words out"},
+    }
+
+
+# ------------------------------------------------------------------------------------------------ K1 alone
+def run_fk(ctx, args, steps):
+    """aa_rx_sg_tf_batch_dev (north_star kernel 1, SURVEY.md 8a row a5 batched): 2^20 right-arm configurations, world
+    poses of the 17 frames that move with the arm, float planes out.  HBM-bound: 28 B in + 17 x 28 B out per unit."""
+    torch = ctx.torch
+    from tmkit_b200 import amino as A
+    from tmkit_b200 import scenes as S
+    from tmkit_b200 import workloads as W
+    sc = S.baxter_sussman()
+    sg = A.SceneGraph.from_scene(sc)
+    q0 = S.q0_vector(sc)
+    sub = sg.config_indices(S.RIGHT_ARM)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    n = N_CFG
+    # the frames the varied joints move: everything below right_s0 in the tree
+    names = sg.frame_names()
+    moving, frames = {sg.frame_id("right_s0")}, []
+    for i in range(sg.frame_count()):
+        if i in moving or sg.frame_parent(i) in moving:
+            moving.add(i)
+            frames.append(i)
+    ring = [torch.from_numpy(np.ascontiguousarray(W.random_configs(lim, n, seed=300 + r).T.astype(np.float32))).to(ctx.dev) for r in range(4)]
+    out = torch.zeros((len(frames) * 7, n), dtype=torch.float32, device=ctx.dev)
+    rows = torch.zeros((n, len(frames), 7), dtype=torch.float64, device=ctx.dev)
+    ts = torch.cuda.Stream(device=ctx.dev)
+
+    def timed(fn, k):
+        with torch.cuda.stream(ts):
+            for i in range(3):
+                fn(i)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ts.synchronize()
+            ev[0].record(ts)
+            for i in range(k):
+                fn(i)
+            ev[1].record(ts)
+            ts.synchronize()
+        return ev[0].elapsed_time(ev[1]) / k
+
+    ms = timed(lambda i: sg.tf_batch_dev(n, sub, q0, ring[i % 4].data_ptr(), A.Q_SOA_F32, n, frames, out.data_ptr(), A.TF_SOA_F32, n,
+                                         ts.cuda_stream), steps)
+    ms_rows = timed(lambda i: sg.tf_batch_dev(n, sub, q0, ring[i % 4].data_ptr(), A.Q_SOA_F32, n, frames, rows.data_ptr(), A.TF_ROWS_F64, 0,
+                                              ts.cuda_stream), max(3, steps // 4))
+    # end to end: host double rows in, host double transforms out (aa_rx_sg_tf_batch), a 2^16 sample
+    m = 1 << 16
+    Qh = W.random_configs(lim, m, seed=9)
+    sg.tf_batch(sub, q0, Qh[:1024], frames=frames)
+    t0 = time.perf_counter()
+    sg.tf_batch(sub, q0, Qh, frames=frames)
+    e2e = m / (time.perf_counter() - t0)
+    ctx.barrier()
+    if ctx.rank != 0:
+        return None
+    hbm_peak, peak_kind, _ = load_peaks()
+    bytes_unit = 4.0 * len(sub) + 28.0 * len(frames)
+    gbs = bytes_unit * n / (ms * 1e-3) / 1e9
+    flops_unit = 61.0 * len(frames) + 34.0 * len(sub)  # SURVEY.md 8d FK term: 61 per moving frame + 34 per revolute joint
+    return {
+        "metric": "batched forward kinematics, configs/sec (aa_rx_sg_tf_batch_dev, 17 moving frames of the right arm)",
+        "value": n / (ms * 1e-3), "unit": "configs/s", "n_gpus": 1, "steps": steps, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "north_star kernel (1): 2^20 right-arm configurations, SoA float joints in, 17 x 7 float planes out",
+                   "frames": len(frames)},
+        "value_f64_rows_out": n / (ms_rows * 1e-3),
+        "e2e": {"value": e2e, "unit": "configs/s", "h2d_bytes_per_step": m * len(sub) * 8, "d2h_bytes_per_step": m * len(frames) * 56,
+                "call": "aa_rx_sg_tf_batch (host double rows in and out, 2^16 configurations)"},
+        "gpu_launches": steps,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                     "kernel": "k_fk_frames<TMK_TF_SOA_F32>", "kernel_ms": ms, "bytes_per_unit": bytes_unit,
+                     "algorithmic_bytes": bytes_unit * n, "peak_kind": peak_kind, "flops_per_unit": flops_unit},
     }
 
 
@@ -738,6 +812,9 @@ def main():
                         sec[wl] = run_sussman(args, steps=min(args.steps, 20))
                     except Exception as e:  # the secondary block never takes the headline line down with it
                         sec[wl] = {"metric": metric_name(wl), "error": repr(e)[:300]}
+                continue
+            if wl == "fk":
+                sec[wl] = run_fk(ctx, args, min(args.steps, 50))
                 continue
             s_steps = min(args.steps, 5 * ctx.world) if wl == "clutter" else min(args.steps, 50)
             sec[wl] = run_workload(ctx, args, wl, max(3, s_steps), 3, 5.0)

@@ -160,6 +160,16 @@ void aa_rx_sg_tf_batch(const struct aa_rx_sg *sg, size_t n_cfg, size_t n_sub, co
                        size_t n_q, const double *q_all_base, const double *Q_sub, size_t ldQ, size_t n_frames,
                        const aa_rx_frame_id *frames, double *TF_abs_out);
 
+/* The same on device buffers, asynchronous on `stream` (NULL = the default stream).  dQ: the sub-configurations in one of
+ * the TMK_Q_* layouts; dTF: TMK_TF_ROWS_F64 = double TF[c][k][7] (the host layout above; ld_tf unused) or
+ * TMK_TF_SOA_F32 = float component planes TF[(k * 7 + i) * ld_tf + c], ld_tf >= n_cfg (coalesced: the layout to keep
+ * transforms in on the device). */
+#define TMK_TF_ROWS_F64 0
+#define TMK_TF_SOA_F32 1
+void aa_rx_sg_tf_batch_dev(const struct aa_rx_sg *sg, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                           size_t n_q, const double *q_all_base, const void *dQ, int layout, size_t ld, size_t n_frames,
+                           const aa_rx_frame_id *frames, void *dTF, int tf_layout, size_t ld_tf, void *stream);
+
 /* Validity of n_cfg configurations; host buffers; blocking.  Returns the number of colliding
  * configurations. */
 size_t aa_rx_cl_check_batch(struct aa_rx_cl *cl, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,

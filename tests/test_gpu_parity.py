@@ -122,6 +122,39 @@ def test_fk_batch_fp32(gpu_sussman):
     np.testing.assert_array_equal(out2, out[:, frames, :])
 
 
+def test_fk_batch_device_entry_point_all_layouts(gpu_sussman):
+    """aa_rx_sg_tf_batch_dev: every input layout x both output layouts agree with the host call and with the oracle
+    (FK within 1e-5 relative, north_star); a canary guards the planes' tail"""
+    import torch
+    sc, orc, sg, cl, q0 = gpu_sussman
+    sub = sg.config_indices(S.RIGHT_ARM)
+    lim = W.arm_limit_table(S.RIGHT_ARM)
+    n = 5000 + 13
+    Q = W.random_configs(lim, n, seed=6)
+    frames = [sg.frame_id(f) for f in ("right_endpoint", "right_w1", "block_a", "right_s0", "right_e1")]
+    want = sg.tf_batch(sub, q0, Q, frames=frames)
+    for c in range(0, n, 501):
+        _, ab = orc.fk(sg.config_set(sub, Q[c], q0))
+        ok, err = tf_close(want[c], ab[frames], FK_RTOL)
+        assert ok, (c, err)
+    ins = {A.Q_ROWS_F64: (torch.from_numpy(Q).cuda(), len(sub)),
+           A.Q_ROWS_F32: (torch.from_numpy(Q.astype(np.float32)).cuda(), len(sub)),
+           A.Q_SOA_F32: (torch.from_numpy(np.ascontiguousarray(Q.T.astype(np.float32))).cuda(), n)}
+    s = torch.cuda.current_stream().cuda_stream
+    for layout, (dq, ld) in ins.items():
+        rows = torch.zeros((n, len(frames), 7), dtype=torch.float64, device="cuda")
+        sg.tf_batch_dev(n, sub, q0, dq.data_ptr(), layout, ld, frames, rows.data_ptr(), A.TF_ROWS_F64, 0, s)
+        ld_tf = n + 19
+        planes = torch.full((len(frames) * 7, ld_tf), 777.0, dtype=torch.float32, device="cuda")
+        sg.tf_batch_dev(n, sub, q0, dq.data_ptr(), layout, ld, frames, planes.data_ptr(), A.TF_SOA_F32, ld_tf, s)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(rows.cpu().numpy(), want)
+        p = planes.cpu().numpy()
+        assert (p[:, n:] == 777.0).all()
+        got = p[:, :n].reshape(len(frames), 7, n).transpose(2, 0, 1)
+        np.testing.assert_array_equal(got.astype(np.float64), want)
+
+
 def test_rel_tf_and_reparent(gpu_sussman):
     """pick: re-hang block_c under the grasp frame (demo/tmpexec.c:317-336); world poses must not move."""
     sc, orc, sg, cl, q0 = gpu_sussman

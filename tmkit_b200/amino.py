@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TMK_LIB") or os.path.join(HERE, "libtmkcl.so")  # TMK_LIB: A/B builds while tuning
 
 Q_ROWS_F64, Q_ROWS_F32, Q_SOA_F32 = 0, 1, 2
+TF_ROWS_F64, TF_SOA_F32 = 0, 1
 
 _vp, _sz, _i, _d = C.c_void_p, C.c_size_t, C.c_int, C.c_double
 _cs = C.c_char_p
@@ -76,6 +77,7 @@ SIGNATURES = {
     "aa_rx_cl_set_set": (None, [_vp, _i, _i, _i]),
     "aa_rx_cl_set_fill": (None, [_vp, _vp]),
     "aa_rx_sg_tf_batch": (None, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _sz, _vp, _vp]),
+    "aa_rx_sg_tf_batch_dev": (None, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _i, _sz, _sz, _vp, _vp, _i, _sz, _vp]),
     "aa_rx_cl_check_batch": (_sz, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
     "aa_rx_cl_check_batch_f32": (_sz, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
     "aa_rx_cl_check_edges": (_sz, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _d, _vp, _vp]),
@@ -403,6 +405,15 @@ class SceneGraph:
         self.L.aa_rx_sg_tf_batch(self.h, Q.shape[0], len(sub), _p(sub), len(qb), _p(qb), _p(Q), Q.shape[1],
                                  n_out, _p(fr), _p(out))
         return out
+
+    def tf_batch_dev(self, n, sub_ids, q_base, dQ: int, layout: int, ld: int, frames, dTF: int, tf_layout: int, ld_tf: int,
+                     stream: int = 0):
+        """aa_rx_sg_tf_batch_dev: raw device addresses in and out, asynchronous on `stream`."""
+        sub = np.ascontiguousarray(sub_ids, dtype=np.int32)
+        qb = _f64(q_base)
+        fr = None if frames is None else np.ascontiguousarray(frames, dtype=np.int32)
+        self.L.aa_rx_sg_tf_batch_dev(self.h, n, len(sub), _p(sub), len(qb), _p(qb), dQ, layout, ld,
+                                     0 if fr is None else len(fr), _p(fr), dTF, tf_layout, ld_tf, stream or None)
 
     # -- mutation ------------------------------------------------------------------
     def copy(self) -> "SceneGraph":

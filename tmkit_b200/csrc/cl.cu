@@ -168,7 +168,16 @@ template <typename T> static void upload(DBuf &b, const std::vector<T> &v, cudaS
 }
 
 /* ------------------------------------------------------------------ scene-graph device mirror (FK) */
+struct FkImage { /* cached per scene graph and device: rebuilt when the arguments change */
+    std::vector<int> sub, frames;
+    std::vector<double> q_base;
+    uint64_t sg_serial = 0;
+    bool all_frames = false, valid = false;
+    DBuf joints, outs;
+    int n_joint = 0, n_out = 0;
+};
 struct SgDev {
+    FkImage *fk = nullptr;     /* tables of aa_rx_sg_tf_batch for the last (sub_ids, q_base, frames) */
     DBuf frames, q, rel, ab;
     DBuf b_frames, b_q, b_out; /* aa_rx_sg_tf_batch scratch */
     DBuf ik_in, ik_out;        /* tmk_dev_ik: one upload, one launch, one download per goal */
@@ -191,6 +200,7 @@ extern "C" void tmk_dev_sg_release(void *dev) {
         d->frames.release(); d->q.release(); d->rel.release(); d->ab.release();
         d->b_frames.release(); d->b_q.release(); d->b_out.release();
         d->ik_in.release(); d->ik_out.release();
+        if (d->fk) { d->fk->joints.release(); d->fk->outs.release(); delete d->fk; }
         delete d;
     }
     cudaSetDevice(cur);
@@ -389,7 +399,7 @@ struct ImageDev {
     uint64_t allow_serial = 0;
     bool valid = false;
     uint64_t serial = 0; /* bumped whenever the image is rebuilt: cached CUDA graphs refer to its buffers */
-    TileCfg wcfg, wcfg_e;
+    TileCfg wcfg, wcfg_e, wcfg_flat;
 };
 
 struct aa_rx_cl {
@@ -1122,6 +1132,12 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     grid.c4 = (const float4 *)im.g_c4.p;
     grid.n_items = grid.on ? (int)n_gridded : 0;
     im.d.grid = im.f.grid = grid;
+    {
+        TileCfg tmp; /* the flat edge source shares the level source's plan; its kernels need the same attributes */
+        if (grid.on) tile_configure(tmp, im.f, n_jslab, k_states_tile<SrcEdgeFlat, SinkEdgeFirst, 256, true>, k_states_tile<SrcEdgeFlat, SinkEdgeFirst, 128, true>);
+        else tile_configure(tmp, im.f, n_jslab, k_states_tile<SrcEdgeFlat, SinkEdgeFirst, 256, false>, k_states_tile<SrcEdgeFlat, SinkEdgeFirst, 128, false>);
+        im.wcfg_flat = tmp;
+    }
     if (grid.on) {
         tile_configure(im.wcfg, im.f, n_jslab, k_states_tile<SrcConfigs, SinkBits, 256, true>,
                        k_states_tile<SrcConfigs, SinkBits, 128, true>);
@@ -1133,7 +1149,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         tile_configure(im.wcfg_e, im.f, n_jslab, k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 256, false>,
                        k_states_tile<SrcEdgeLevel, SinkEdgeFirst, 128, false>);
     }
-    if (mg.size() > 64) im.wcfg.smem = im.wcfg_e.smem = -1; /* queue items hold a 6-bit moving-geometry index */
+    if (mg.size() > 64) im.wcfg.smem = im.wcfg_e.smem = im.wcfg_flat.smem = -1; /* queue items hold a 6-bit moving-geometry index */
     if (getenv("TMK_DEBUG_IMAGE"))
         fprintf(stderr, "tmkcl tile: configs TILE %d, %d B shared memory, grid %d | edges TILE %d, %d B, grid %d\n", im.wcfg.tile,
                 im.wcfg.smem, im.wcfg.grid, im.wcfg_e.tile, im.wcfg_e.smem, im.wcfg_e.grid);
@@ -1416,11 +1432,42 @@ static void launch_configs(struct aa_rx_cl *cl, size_t n_cfg, const void *dQ, in
 
 static void launch_edges(struct aa_rx_cl *cl, size_t n_edge, const void *dQ0, const void *dQ1, int layout, size_t ld,
                          double seg_len, uint32_t *d_bits, int32_t *d_first, cudaStream_t s,
-                         int n_levels = TMK_EDGE_LEVELS) {
+                         int n_levels = TMK_EDGE_LEVELS, size_t flat_states = 0) {
     ImageDev &im = cl->img;
     if (!(seg_len > 0)) tmk_die("edges: seg_len must be positive");
     if (n_edge > 0x7ffffff0u) tmk_die("edges: more than 2^31 edges in one call");
     DevStats *st = cl->stats_on ? (DevStats *)cl->d_stats.p : nullptr;
+    if (flat_states && cl->use_tile && im.wcfg_flat.smem > 0 && !st && n_edge <= 4096 && !getenv("TMK_NO_FLAT")) {
+        /* small batch (the caller bounded its states): every state of every edge in one tile launch, six launches in
+         * all instead of the ~20 dependent ones of the level pipeline */
+        UncList u = unc_list(cl, flat_states + 1024, s, true);
+        const uint32_t ne = (uint32_t)n_edge;
+        cl->d_nd.need(sizeof(int32_t) * (n_edge + 1));
+        cl->d_efirst.need(sizeof(int32_t) * (n_edge + 1));
+        cl->d_alive0.need(sizeof(uint32_t) * (n_edge + 2));
+        int32_t *nd = (int32_t *)cl->d_nd.p, *first = (int32_t *)cl->d_efirst.p;
+        uint32_t *off = (uint32_t *)cl->d_alive0.p, *cnt = (uint32_t *)cl->d_cnt.p;
+        cudaEvent_t *ev = timing_begin(cl, s);
+        k_edges_prep_flat<<<1, 1024, 0, s>>>(dQ0, dQ1, layout, ld, im.f.n_sub, ne, seg_len, nd, first, im.f.static_hit, off);
+        SrcEdgeFlat src;
+        src.lv.p0 = dQ0; src.lv.p1 = dQ1; src.lv.layout = layout; src.lv.ld = ld; src.lv.nd = nd; src.lv.n_edge = ne;
+        src.lv.alive = nullptr; src.lv.n_alive = nullptr; src.lv.level = 0;
+        src.off = off;
+        SinkEdgeFirst sink;
+        sink.first = first;
+        const TileCfg &cfg = im.wcfg_flat;
+        const unsigned grid = (unsigned)std::min<size_t>((flat_states + cfg.tile - 1) / cfg.tile + 1, (size_t)cfg.grid);
+        launch_tile<SrcEdgeFlat, SinkEdgeFirst>(im.f, cfg, src, sink, u, (unsigned long long *)(cnt + 2), grid, s);
+        k_heavy_mixed<SrcEdgeLevel, SinkEdgeFirst><<<148, 128, 0, s>>>(im.f, src.lv, sink, u);
+        if (ev) CK(cudaEventRecord(ev[1], s));
+        k_recheck_items<SrcEdgeLevel, SinkEdgeFirst><<<148 * 3, 128, 0, s>>>(im.d, src.lv, sink, u);
+        k_edges_overflow_all<<<148 * 2, 128, 0, s>>>(im.d, src.lv, u, first);
+        k_edges_finish<<<(ne + 255) / 256, 256, 0, s>>>(first, ne, d_bits, d_first);
+        CK(cudaGetLastError());
+        if (ev) CK(cudaEventRecord(ev[2], s));
+        cl->stats.n_launches += 6;
+        return;
+    }
     const size_t small = getenv("TMK_EDGE_SMALL") ? (size_t)atol(getenv("TMK_EDGE_SMALL")) : 0; /* tuning aid */
     if (cl->use_tile && im.wcfg_e.smem > 0 && !st && n_edge >= small) {
         /* fast path: bisection levels through the tile pipeline (pipeline.cuh), replayed from a CUDA graph */
@@ -1681,8 +1728,9 @@ static void edges_host_begin(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, c
      * are launches the host can see and skip.  +2 segments of slack: the device count is authoritative (an edge
      * that needs more levels than were launched raises the overflow flag, see k_edges_prep). */
     int n_levels = TMK_EDGE_LEVELS;
+    size_t flat_states = 0; /* > 0: an upper bound of the batch's states, small enough for the one-launch path */
     if (n_edge && n_edge <= 4096 && seg_len > 0) {
-        double s2max = 0;
+        double s2max = 0, states = 0;
         for (size_t e = 0; e < n_edge; e++) {
             double s2 = 0;
             for (size_t k = 0; k < n_sub; k++) {
@@ -1690,7 +1738,9 @@ static void edges_host_begin(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, c
                 s2 += dq * dq;
             }
             if (s2 > s2max) s2max = s2;
+            states += ceil(sqrt(s2) / seg_len) + 2; /* the device count is authoritative; this bounds the launch */
         }
+        if (states <= 49152.0) flat_states = (size_t)states;
         const double nd_max = ceil(sqrt(s2max) / seg_len) + 2;
         if (nd_max < (double)(1 << (TMK_EDGE_LEVELS - 1))) {
             int L = 1; /* positions 2^(L-1) .. 2^L - 1 live at level L */
@@ -1699,7 +1749,7 @@ static void edges_host_begin(struct aa_rx_cl *cl, size_t n_edge, size_t n_sub, c
         }
     }
     launch_edges(cl, n_edge, cl->d_q.p, cl->d_q1.p, TMK_Q_ROWS_F64, ldQ, seg_len, (uint32_t *)cl->d_bits.p,
-                 first_invalid ? (int32_t *)cl->d_first.p : nullptr, cl->stream, n_levels);
+                 first_invalid ? (int32_t *)cl->d_first.p : nullptr, cl->stream, n_levels, flat_states);
     if (nw) CK(cudaMemcpyAsync(valid_bits, cl->d_bits.p, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, cl->stream));
     if (first_invalid && n_edge)
         CK(cudaMemcpyAsync(first_invalid, cl->d_first.p, sizeof(int32_t) * n_edge, cudaMemcpyDeviceToHost, cl->stream));
@@ -1843,71 +1893,116 @@ extern "C" void aa_rx_cl_stats_enable(struct aa_rx_cl *cl, int enable) { cl->sta
 extern "C" void aa_rx_cl_batch_stats(struct aa_rx_cl *cl, struct tmk_batch_stats *out) { *out = cl->stats; }
 
 /* ------------------------------------------------------------------ K1 standalone: batched FK */
+
+static FkImage *fk_image(const struct aa_rx_sg *sg, size_t n_sub, const aa_rx_config_id *sub_ids, size_t n_q,
+                         const double *q_base, size_t n_frames, const aa_rx_frame_id *frames) {
+    if (!sg || !sg->inited) tmk_die("aa_rx_sg_tf_batch: scene graph not initialised");
+    if (n_q != sg->n_q) tmk_die("aa_rx_sg_tf_batch: n_q mismatch");
+    if (n_sub > TMK_MAXSUB) tmk_die("aa_rx_sg_tf_batch: n_sub = %zu > %d", n_sub, TMK_MAXSUB);
+    SgDev *sd = sg_dev(sg);
+    if (!sd->fk) sd->fk = new FkImage();
+    FkImage *im = sd->fk;
+    const size_t n_f = sg->n_f;
+    const bool all = frames == nullptr;
+    bool same = im->valid && im->sg_serial == sg->serial && im->all_frames == all && im->sub.size() == n_sub &&
+                0 == memcmp(im->sub.data(), sub_ids, sizeof(int) * n_sub) && 0 == memcmp(im->q_base.data(), q_base, sizeof(double) * n_q) &&
+                (all || (im->frames.size() == n_frames && 0 == memcmp(im->frames.data(), frames, sizeof(int) * n_frames)));
+    if (same) return im;
+    for (size_t k = 0; k < n_sub; k++)
+        if (sub_ids[k] < 0 || (size_t)sub_ids[k] >= n_q) tmk_die("aa_rx_sg_tf_batch: bad configuration id %d", sub_ids[k]);
+    std::vector<double> rel(7 * n_f), ab(7 * n_f);
+    tmk_dev_fk64(sg, q_base, rel.data(), ab.data());
+    /* fold the fixed (and the not-varied) frames into the varied joint they hang on: the collision image's rule */
+    std::vector<int> slot(n_f, -1);
+    std::vector<double> fold(7 * n_f, 0.0);
+    std::vector<DJoint<float>> joints;
+    for (size_t i = 0; i < n_f; i++) {
+        const int p = sg->parent[i];
+        int qs = -1;
+        if (sg->type[i] != TMK_FIXED)
+            for (size_t k = 0; k < n_sub; k++)
+                if (sub_ids[k] == sg->qidx[i]) qs = (int)k;
+        if (qs >= 0) {
+            DJoint<double> J;
+            memset(&J, 0, sizeof(J));
+            const double *E = sg->E + 7 * i;
+            if (p < 0) { memcpy(J.E, E, sizeof(double) * 7); J.parent = -1; }
+            else if (slot[p] < 0) { tmk_tfmul(&ab[7 * p], E, J.E); J.parent = -1; }
+            else { tmk_tfmul(&fold[7 * p], E, J.E); J.parent = slot[p]; }
+            memcpy(J.ax, sg->axis + 3 * i, sizeof(double) * 3);
+            J.off = sg->offset[i]; J.type = sg->type[i]; J.qslot = qs;
+            slot[i] = (int)joints.size();
+            DJoint<float> Jf;
+            cvt_joint(J, Jf);
+            joints.push_back(Jf);
+            const double id7[7] = {0, 0, 0, 1, 0, 0, 0};
+            memcpy(&fold[7 * i], id7, sizeof(id7));
+        } else if (p >= 0 && slot[p] >= 0) {
+            slot[i] = slot[p];
+            tmk_tfmul(&fold[7 * p], &rel[7 * i], &fold[7 * i]);
+        }
+    }
+    if (joints.size() > TMK_MAXJ) tmk_die("aa_rx_sg_tf_batch: %zu varied joints > %d", joints.size(), TMK_MAXJ);
+    const size_t n_out = all ? n_f : n_frames;
+    std::vector<FkOut> outs(n_out);
+    for (size_t k = 0; k < n_out; k++) {
+        const int f = all ? (int)k : frames[k];
+        if (f < 0 || (size_t)f >= n_f) tmk_die("aa_rx_sg_tf_batch: bad frame id %d", f);
+        const double *src = slot[f] >= 0 ? &fold[7 * (size_t)f] : &ab[7 * (size_t)f];
+        for (int i = 0; i < 7; i++) outs[k].tf[i] = (float)src[i];
+        outs[k].slot = slot[f];
+    }
+    CK(cudaDeviceSynchronize()); /* launches in flight may still read the old tables */
+    upload(im->joints, joints, 0);
+    upload(im->outs, outs, 0);
+    CK(cudaDeviceSynchronize());
+    im->n_joint = (int)joints.size(); im->n_out = (int)n_out;
+    im->sub.assign(sub_ids, sub_ids + n_sub);
+    im->q_base.assign(q_base, q_base + n_q);
+    im->frames.clear();
+    if (!all) im->frames.assign(frames, frames + n_frames);
+    im->all_frames = all; im->sg_serial = sg->serial; im->valid = true;
+    return im;
+}
+
+extern "C" void aa_rx_sg_tf_batch_dev(const struct aa_rx_sg *sg, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
+                                      size_t n_q, const double *q_all_base, const void *dQ, int layout, size_t ld,
+                                      size_t n_frames, const aa_rx_frame_id *frames, void *dTF, int tf_layout, size_t ld_tf,
+                                      void *stream) {
+    if (layout < 0 || layout > 2) tmk_die("aa_rx_sg_tf_batch_dev: unknown layout %d", layout);
+    if (tf_layout == TMK_TF_SOA_F32 && ld_tf < n_cfg) tmk_die("aa_rx_sg_tf_batch_dev: ld_tf < n_cfg");
+    FkImage *im = fk_image(sg, n_sub, sub_ids, n_q, q_all_base, n_frames, frames);
+    if (n_cfg == 0 || im->n_out == 0) return;
+    const size_t smem = (((size_t)im->n_joint * sizeof(DJoint<float>) + 15) & ~(size_t)15) + (size_t)im->n_out * sizeof(FkOut);
+    if (smem > 200 * 1024) tmk_die("aa_rx_sg_tf_batch: %d frames exceed the kernel's frame table", im->n_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n_cfg + 255) / 256);
+    if (tf_layout == TMK_TF_SOA_F32) {
+        static bool attr = false;
+        if (!attr) { CK(cudaFuncSetAttribute(k_fk_frames<TMK_TF_SOA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        k_fk_frames<TMK_TF_SOA_F32><<<grid, 256, smem, s>>>((const DJoint<float> *)im->joints.p, im->n_joint, (const FkOut *)im->outs.p, im->n_out,
+                                                         dQ, layout, ld, n_cfg, dTF, ld_tf);
+    } else if (tf_layout == TMK_TF_ROWS_F64) {
+        static bool attr = false;
+        if (!attr) { CK(cudaFuncSetAttribute(k_fk_frames<TMK_TF_ROWS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        k_fk_frames<TMK_TF_ROWS_F64><<<grid, 256, smem, s>>>((const DJoint<float> *)im->joints.p, im->n_joint, (const FkOut *)im->outs.p, im->n_out,
+                                                          dQ, layout, ld, n_cfg, dTF, ld_tf);
+    } else tmk_die("aa_rx_sg_tf_batch_dev: unknown output layout %d", tf_layout);
+    CK(cudaGetLastError());
+}
+
 extern "C" void aa_rx_sg_tf_batch(const struct aa_rx_sg *sg, size_t n_cfg, size_t n_sub, const aa_rx_config_id *sub_ids,
                                   size_t n_q, const double *q_all_base, const double *Q_sub, size_t ldQ,
                                   size_t n_frames, const aa_rx_frame_id *frames, double *TF_abs_out) {
-    if (!sg || !sg->inited) tmk_die("aa_rx_sg_tf_batch: scene graph not initialised");
-    if (n_q != sg->n_q) tmk_die("aa_rx_sg_tf_batch: n_q mismatch");
     if (ldQ < n_sub) tmk_die("aa_rx_sg_tf_batch: ldQ < n_sub");
-    size_t n_f = sg->n_f;
-    std::vector<FFrame> fr(n_f);
-    size_t n_out = frames ? n_frames : n_f;
-    for (size_t i = 0; i < n_f; i++) {
-        FFrame &F = fr[i];
-        for (int k = 0; k < 7; k++) F.E[k] = (float)sg->E[7 * i + k];
-        for (int k = 0; k < 3; k++) F.ax[k] = (float)sg->axis[3 * i + k];
-        F.off = (float)sg->offset[i];
-        F.parent = sg->parent[i];
-        F.type = sg->type[i];
-        F.qslot = -1;
-        F.qbase = 0;
-        if (F.type) {
-            F.qbase = (float)q_all_base[sg->qidx[i]];
-            for (size_t k = 0; k < n_sub; k++)
-                if (sub_ids[k] == sg->qidx[i]) F.qslot = (int)k;
-        }
-        F.out = frames ? -1 : (int)i;
-    }
-    if (frames)
-        for (size_t k = 0; k < n_frames; k++) {
-            if (frames[k] < 0 || (size_t)frames[k] >= n_f) tmk_die("aa_rx_sg_tf_batch: bad frame id %d", frames[k]);
-            fr[frames[k]].out = (int)k;
-        }
-    if (n_cfg == 0 || n_out == 0) return;
-    /* only the requested frames and their ancestors are evaluated (an IK chain in a scene with hundreds of
-     * obstacle frames is still ~20 frames) */
-    std::vector<char> need(n_f, frames ? 0 : 1);
-    if (frames)
-        for (size_t i = n_f; i-- > 0;) {
-            if (fr[i].out >= 0) need[i] = 1;
-            if (need[i] && fr[i].parent >= 0) need[fr[i].parent] = 1;
-        }
-    std::vector<int> remap(n_f, -1);
-    std::vector<FFrame> sel;
-    for (size_t i = 0; i < n_f; i++)
-        if (need[i]) {
-            remap[i] = (int)sel.size();
-            FFrame F = fr[i];
-            if (F.parent >= 0) F.parent = remap[F.parent]; /* parents precede children */
-            sel.push_back(F);
-        }
-    const size_t n_sel = sel.size();
-    int T = 64;
-    size_t smem = 0;
-    for (;; T /= 2) {
-        smem = ((sizeof(FFrame) * n_sel + 15) & ~(size_t)15) + sizeof(float) * 7 * n_sel * (size_t)T;
-        if (smem <= 200 * 1024) break;
-        if (T == 8) tmk_die("aa_rx_sg_tf_batch: %zu frames exceed the shared-memory slab", n_sel);
-    }
+    FkImage *im = fk_image(sg, n_sub, sub_ids, n_q, q_all_base, n_frames, frames);
+    if (n_cfg == 0 || im->n_out == 0) return;
     SgDev *sd = sg_dev(sg);
-    DBuf &dfr = sd->b_frames, &dq = sd->b_q, &dout = sd->b_out;
-    upload(dfr, sel, 0);
+    DBuf &dq = sd->b_q, &dout = sd->b_out;
     dq.need(n_cfg * ldQ * 8);
+    dout.need(n_cfg * (size_t)im->n_out * 7 * 8);
     CK(cudaMemcpyAsync(dq.p, Q_sub, n_cfg * ldQ * 8, cudaMemcpyHostToDevice, 0));
-    dout.need(n_cfg * n_out * 7 * 8);
-    CK(cudaFuncSetAttribute(k_fk_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_fk_batch<<<(unsigned)((n_cfg + T - 1) / T), T, smem>>>((const FFrame *)dfr.p, (int)n_sel, (const double *)dq.p, ldQ,
-                                                             n_cfg, (int)n_out, (double *)dout.p);
-    CK(cudaGetLastError());
-    CK(cudaMemcpy(TF_abs_out, dout.p, n_cfg * n_out * 7 * 8, cudaMemcpyDeviceToHost));
+    aa_rx_sg_tf_batch_dev(sg, n_cfg, n_sub, sub_ids, n_q, q_all_base, dq.p, TMK_Q_ROWS_F64, ldQ, n_frames, frames, dout.p,
+                          TMK_TF_ROWS_F64, 0, nullptr);
+    CK(cudaMemcpy(TF_abs_out, dout.p, n_cfg * (size_t)im->n_out * 7 * 8, cudaMemcpyDeviceToHost));
 }

@@ -1,7 +1,7 @@
 /* kernels.cuh - device tables shared by all kernels, and the kernels that are NOT the batch pipeline
  * (that one lives in pipeline.cuh):
- *   k_fk_batch            K1 standalone (aa_rx_sg_tf_batch): one thread per configuration, FP32 chain over
- *                         the full frame table staged in shared memory, writes the requested frames
+ *   k_fk_frames           K1 standalone (aa_rx_sg_tf_batch[_dev]): one thread per configuration, FP32 chain over the
+ *                         varied joints (fixed frames folded on the host), one product per requested frame
  *   k_fk_single64         aa_rx_sg_tf: one configuration, double
  *   k_pairs_tf64          aa_rx_cl_check / allow_config / hoisted static pairs: one thread per geometry
  *                         pair on caller-provided absolute transforms, double
@@ -307,51 +307,50 @@ __global__ void k_fk_single64(const DFrame *fr, int n_f, const double *q, double
     }
 }
 
-/* K1 standalone: batched FK, one thread per configuration, FP32 arithmetic, writes the requested
- * frames' absolute transforms as doubles (aa_rx_sg_tf_batch).  Frame parameters staged in shared
- * memory as floats; per-thread running poses live in a shared-memory slab [frame][7][thread]. */
-struct FFrame {
-    float E[7];
-    float ax[3];
-    float off;
-    int parent, type, qslot; /* qslot: index into the sub-configuration, or -1 = use qbase */
-    float qbase;
-    int out; /* output slot or -1 */
+/* K1 standalone (aa_rx_sg_tf_batch, aa_rx_sg_tf_batch_dev): one thread = one configuration.  The host folds every
+ * fixed frame into the varied joint it hangs on (exactly as the collision image does), so the device work is the
+ * chain of the <= TMK_MAXJ varied joints plus ONE transform product per requested frame: pose(frame) =
+ * pose(joint slot) * fold(frame); frames no varied joint moves are constants.  Joint values come through load_q
+ * (SoA float: one coalesced 128-byte transaction per joint and warp).  Output either as component planes
+ * [frame * 7 + k][configuration] in float (coalesced: the layout to keep on the device) or as the dense double rows
+ * [configuration][frame][7] of the host ABI. */
+struct FkOut {
+    float tf[7]; /* slot >= 0: pose relative to that joint | slot < 0: the constant world pose */
+    int slot;
 };
+#define TMK_TF_ROWS_F64 0
+#define TMK_TF_SOA_F32 1
 
-__global__ void k_fk_batch(const FFrame *fr_g, int n_f, const double *Q, size_t ldQ, size_t n_cfg, int n_out,
-                           double *out) {
-    extern __shared__ unsigned char smem_raw[];
-    FFrame *fr = (FFrame *)smem_raw;
-    float *slab = (float *)(smem_raw + ((sizeof(FFrame) * (size_t)n_f + 15) & ~(size_t)15));
-    for (int i = threadIdx.x; i < n_f * (int)(sizeof(FFrame) / 4); i += blockDim.x)
-        ((uint32_t *)fr)[i] = ((const uint32_t *)fr_g)[i];
+template <int TF_LAYOUT>
+__global__ void __launch_bounds__(256) k_fk_frames(const DJoint<float> *joints, int n_joint, const FkOut *outs, int n_out, const void *Q,
+                                                   int layout, size_t ld, size_t n_cfg, void *TF, size_t ld_tf) {
+    extern __shared__ __align__(16) unsigned char fk_smem[];
+    DJoint<float> *J = (DJoint<float> *)fk_smem;
+    FkOut *O = (FkOut *)(fk_smem + (((size_t)n_joint * sizeof(DJoint<float>) + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < n_joint * (int)(sizeof(DJoint<float>) / 4); i += blockDim.x) ((uint32_t *)J)[i] = ((const uint32_t *)joints)[i];
+    for (int i = threadIdx.x; i < n_out * (int)(sizeof(FkOut) / 4); i += blockDim.x) ((uint32_t *)O)[i] = ((const uint32_t *)outs)[i];
     __syncthreads();
-    size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (c >= n_cfg) return;
-    const int T = blockDim.x, tid = threadIdx.x;
-    for (int i = 0; i < n_f; i++) {
-        const FFrame &F = fr[i];
-        Xf<float> E = xload(F.E);
-        Xf<float> r = E;
-        if (F.type) {
-            float q = F.qslot >= 0 ? (float)Q[c * ldQ + F.qslot] : F.qbase;
-            r = fk_joint(E, mk<float>(F.ax[0], F.ax[1], F.ax[2]), F.off, F.type, q, (const Xf<float> *)nullptr);
-        }
-        Xf<float> a = r;
-        if (F.parent >= 0) {
-            const float *pp = slab + (size_t)F.parent * 7 * T + tid;
-            Xf<float> P;
-            P.r.x = pp[0]; P.r.y = pp[T]; P.r.z = pp[2 * T]; P.r.w = pp[3 * T];
-            P.v.x = pp[4 * T]; P.v.y = pp[5 * T]; P.v.z = pp[6 * T];
-            a = xmul(P, r);
-        }
-        float *po = slab + (size_t)i * 7 * T + tid;
-        po[0] = a.r.x; po[T] = a.r.y; po[2 * T] = a.r.z; po[3 * T] = a.r.w;
-        po[4 * T] = a.v.x; po[5 * T] = a.v.y; po[6 * T] = a.v.z;
-        if (F.out >= 0) {
-            double *o = out + (c * (size_t)n_out + (size_t)F.out) * 7;
-            o[0] = a.r.x; o[1] = a.r.y; o[2] = a.r.z; o[3] = a.r.w; o[4] = a.v.x; o[5] = a.v.y; o[6] = a.v.z;
+    Xf<float> jp[TMK_MAXJ];
+    for (int j = 0; j < n_joint; j++) {
+        const DJoint<float> &Jt = J[j];
+        Xf<float> par;
+        if (Jt.parent >= 0) par = jp[Jt.parent];
+        jp[j] = fk_joint(xload(Jt.E), mk<float>(Jt.ax[0], Jt.ax[1], Jt.ax[2]), Jt.off, Jt.type, load_q<float>(Q, layout, ld, c, Jt.qslot),
+                         Jt.parent >= 0 ? &par : (const Xf<float> *)nullptr);
+    }
+    for (int k = 0; k < n_out; k++) {
+        const FkOut &o = O[k];
+        Xf<float> X = xload(o.tf);
+        if (o.slot >= 0) X = xmul(jp[o.slot], X);
+        if (TF_LAYOUT == TMK_TF_SOA_F32) {
+            float *p = (float *)TF + (size_t)k * 7 * ld_tf + c;
+            p[0] = X.r.x; p[ld_tf] = X.r.y; p[2 * ld_tf] = X.r.z; p[3 * ld_tf] = X.r.w;
+            p[4 * ld_tf] = X.v.x; p[5 * ld_tf] = X.v.y; p[6 * ld_tf] = X.v.z;
+        } else {
+            double *p = (double *)TF + (c * (size_t)n_out + (size_t)k) * 7;
+            p[0] = X.r.x; p[1] = X.r.y; p[2] = X.r.z; p[3] = X.r.w; p[4] = X.v.x; p[5] = X.v.y; p[6] = X.v.z;
         }
     }
 }

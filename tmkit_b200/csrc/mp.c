@@ -392,15 +392,22 @@ static size_t point_at(const double *path, const double *cum, size_t n, size_t d
     return i;
 }
 
-/* shortcut_path: MP_K random pairs of points on the path per round (the second within a third of the path length
- * of the first, OMPL's rangeRatio 0.33), one batched check, the non-overlapping valid ones applied by decreasing
- * saving.  *path may be reallocated (every applied shortcut adds up to two vertices).  Returns the new n. */
+/* shortcut_path: MP_SC random pairs of points on the path per round (the second within a third of the path length
+ * of the first, OMPL's rangeRatio 0.33).  A shortcut P0 -> P1 replaces the path between a point of segment i and a
+ * point of segment j > i; the two stubs it leaves (vertex i -> P0, P1 -> vertex j+1) are sub-segments of validated
+ * edges, but a discretised check of a sub-segment samples other states than the check of the segment did - so all
+ * three edges of every candidate go into the round's ONE batched check and a candidate counts only if all three are
+ * valid (OMPL validates the repaired path afterwards, checkAndRepair; here nothing invalid is ever inserted).  The valid
+ * candidates are applied by decreasing saving as long as they do not overlap and keep a vertex between them.
+ * *path may be reallocated (every applied shortcut adds up to two vertices).  Returns the new n. */
+#define MP_SC 96
 static size_t shortcut_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
     const size_t dim = mp->n_sub;
-    double *P0 = (double *)malloc(sizeof(double) * MP_K * dim), *P1 = (double *)malloc(sizeof(double) * MP_K * dim);
-    double d0[MP_K], d1[MP_K], save[MP_K];
-    uint32_t bits[MP_K / 32 + 2];
-    for (int round = 0; round < 4 && n >= 3; round++) {
+    double *E0 = (double *)malloc(sizeof(double) * 3 * MP_SC * dim), *E1 = (double *)malloc(sizeof(double) * 3 * MP_SC * dim);
+    double d0[MP_SC], save[MP_SC];
+    size_t s0[MP_SC], s1[MP_SC];
+    uint32_t bits[3 * MP_SC / 32 + 2];
+    for (int round = 0; round < 2 && n >= 3; round++) {
         double *path = *path_io;
         double *cum = (double *)malloc(sizeof(double) * n);
         cum[0] = 0;
@@ -408,23 +415,32 @@ static size_t shortcut_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
         const double L = cum[n - 1];
         if (!(L > 0)) { free(cum); break; }
         int n_c = 0;
-        for (int k = 0; k < MP_K; k++) {
+        for (int k = 0; k < MP_SC; k++) {
             double a = rng_unit(&mp->rng) * L, b = a + (0.02 + 0.31 * rng_unit(&mp->rng)) * L;
             if (b > L) b = L;
-            const size_t sa = point_at(path, cum, n, dim, a, P0 + n_c * dim), sb = point_at(path, cum, n, dim, b, P1 + n_c * dim);
+            double *P0 = E0 + (size_t)(3 * n_c) * dim, *P1 = E1 + (size_t)(3 * n_c) * dim;
+            const size_t sa = point_at(path, cum, n, dim, a, P0), sb = point_at(path, cum, n, dim, b, P1);
             if (sa == sb) continue; /* both on one segment: nothing to gain */
-            const double direct = dist(P0 + n_c * dim, P1 + n_c * dim, dim);
-            if (b - a - direct < 1e-6 * L) continue;
-            d0[n_c] = a; d1[n_c] = b; save[n_c] = b - a - direct;
+            const double direct = dist(P0, P1, dim);
+            if (b - a - direct < 1e-4 * L) continue;
+            /* edges 3k+1, 3k+2: the stubs vertex sa -> P0 and P1 -> vertex sb+1 */
+            memcpy(E0 + (size_t)(3 * n_c + 1) * dim, path + sa * dim, sizeof(double) * dim);
+            memcpy(E1 + (size_t)(3 * n_c + 1) * dim, P0, sizeof(double) * dim);
+            memcpy(E0 + (size_t)(3 * n_c + 2) * dim, P1, sizeof(double) * dim);
+            memcpy(E1 + (size_t)(3 * n_c + 2) * dim, path + (sb + 1) * dim, sizeof(double) * dim);
+            d0[n_c] = a; s0[n_c] = sa; s1[n_c] = sb; save[n_c] = b - a - direct;
             n_c++;
         }
-        int applied = 0;
+        double saved = 0;
         if (n_c) {
-            check_edges(mp, (size_t)n_c, P0, P1, bits);
-            /* greedy: largest saving first, intervals must not overlap */
-            int order[MP_K], n_ok = 0, take[MP_K], n_take = 0;
-            for (int k = 0; k < n_c; k++)
-                if ((bits[k >> 5] >> (k & 31)) & 1u) order[n_ok++] = k;
+            check_edges(mp, (size_t)(3 * n_c), E0, E1, bits);
+            /* greedy: largest saving first; intervals must not overlap and must keep a vertex between them */
+            int order[MP_SC], n_ok = 0, take[MP_SC], n_take = 0;
+            for (int k = 0; k < n_c; k++) {
+                const uint32_t e = 3u * (uint32_t)k;
+                if (((bits[e >> 5] >> (e & 31)) & 1u) && ((bits[(e + 1) >> 5] >> ((e + 1) & 31)) & 1u) && ((bits[(e + 2) >> 5] >> ((e + 2) & 31)) & 1u))
+                    order[n_ok++] = k;
+            }
             for (int x = 1; x < n_ok; x++) { /* insertion sort by saving, descending */
                 int v = order[x], y = x;
                 while (y > 0 && save[order[y - 1]] < save[v]) { order[y] = order[y - 1]; y--; }
@@ -433,7 +449,7 @@ static size_t shortcut_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
             for (int x = 0; x < n_ok; x++) {
                 const int k = order[x];
                 int clash = 0;
-                for (int y = 0; y < n_take; y++) clash |= !(d1[k] <= d0[take[y]] || d0[k] >= d1[take[y]]);
+                for (int y = 0; y < n_take; y++) clash |= !(s1[k] < s0[take[y]] || s0[k] > s1[take[y]]);
                 if (!clash) take[n_take++] = k;
             }
             if (n_take) {
@@ -446,10 +462,11 @@ static size_t shortcut_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
                 size_t m = 0, i = 0;
                 for (int x = 0; x < n_take; x++) {
                     const int k = take[x];
-                    while (i < n && cum[i] <= d0[k]) { memcpy(out + m * dim, path + i * dim, sizeof(double) * dim); m++; i++; }
-                    memcpy(out + m * dim, P0 + k * dim, sizeof(double) * dim); m++;
-                    memcpy(out + m * dim, P1 + k * dim, sizeof(double) * dim); m++;
-                    while (i < n && cum[i] < d1[k]) i++; /* the vertices the shortcut bypasses */
+                    while (i <= s0[k]) { memcpy(out + m * dim, path + i * dim, sizeof(double) * dim); m++; i++; }
+                    memcpy(out + m * dim, E0 + (size_t)(3 * k) * dim, sizeof(double) * dim); m++;
+                    memcpy(out + m * dim, E1 + (size_t)(3 * k) * dim, sizeof(double) * dim); m++;
+                    i = s1[k] + 1; /* the vertices the shortcut bypasses */
+                    saved += save[k];
                 }
                 while (i < n) { memcpy(out + m * dim, path + i * dim, sizeof(double) * dim); m++; i++; }
                 /* a shortcut point that coincides with a kept vertex would leave a zero-length edge */
@@ -464,41 +481,20 @@ static size_t shortcut_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
                 free(*path_io);
                 *path_io = out;
                 n = w;
-                applied = n_take;
             }
         }
         free(cum);
-        if (!applied) break;
+        if (saved < 0.02 * L) break; /* a further round is a GPU round trip for a few percent */
     }
-    free(P0); free(P1);
+    free(E0); free(E1);
     return n;
 }
 
-/* reduceVertices -> shortcutPath -> reduceVertices -> check of the final path (OMPL: checkAndRepair).  Shortcut
- * end points are new states on old segments: the discretised check of a sub-segment samples other states than the
- * check of the segment did, so the result is validated once more and the vertex-only result kept if it fails. */
+/* reduceVertices -> shortcutPath, OMPL's order */
 static size_t simplify_path(struct aa_rx_mp *mp, double **path_io, size_t n) {
-    const size_t dim = mp->n_sub;
     n = reduce_vertices(mp, *path_io, n);
     if (n < 3) return n;
-    double *safe = (double *)malloc(sizeof(double) * n * dim);
-    memcpy(safe, *path_io, sizeof(double) * n * dim);
-    const size_t n_safe = n;
-    n = shortcut_path(mp, path_io, n);
-    n = reduce_vertices(mp, *path_io, n);
-    int ok = 1;
-    if (n >= 2) {
-        uint32_t *bits = (uint32_t *)calloc(n / 32 + 2, sizeof(uint32_t));
-        ok = check_edges(mp, n - 1, *path_io, *path_io + dim, bits) == 0;
-        free(bits);
-    }
-    if (!ok) {
-        free(*path_io);
-        *path_io = safe;
-        return n_safe;
-    }
-    free(safe);
-    return n;
+    return shortcut_path(mp, path_io, n);
 }
 
 int aa_rx_mp_plan(struct aa_rx_mp *mp, double timeout, size_t *n_path, double **path_all) {

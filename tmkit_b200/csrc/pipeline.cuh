@@ -220,6 +220,31 @@ struct SrcEdgeLevel {
     __device__ __forceinline__ State from_id(uint32_t x, uint32_t y) const { return at(x, (int)y); }
 };
 
+/* Small edge batches (a planner's frontier: a hundred edges of ten states): ALL states of all edges in one launch.
+ * Level by level the batch is a chain of ~20 dependent launches of a few microseconds of work each; without the
+ * early-out of the levels it is a few thousand states - one tile launch.  State s belongs to the edge e with
+ * off[e] <= s < off[e+1] (off = exclusive prefix sum of the segment counts, built by k_edges_prep_flat) at position
+ * s - off[e] of OMPL's test order; first[e] = atomicMin of the invalid positions, exactly as for the levels. */
+struct SrcEdgeFlat {
+    SrcEdgeLevel lv;       /* end points, layout, segment counts: at(), load1(), ids as for the levels */
+    const uint32_t *off;   /* [n_edge + 1] */
+    typedef SrcEdgeLevel::State State;
+    __device__ __forceinline__ size_t count() const { return (size_t)off[lv.n_edge]; }
+    __device__ __forceinline__ State prepare(size_t s) const {
+        const uint32_t n = lv.n_edge;
+        if (s >= (size_t)off[n]) { State st; st.e = 0; st.pos = 0; st.nd = 0; st.t = 1.0; st.live = false; return st; }
+        uint32_t lo = 0, hi = n; /* largest e with off[e] <= s */
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((size_t)off[mid] <= s) lo = mid; else hi = mid;
+        }
+        return lv.at(lo, (int)(s - off[lo]));
+    }
+    template <typename T> __device__ __forceinline__ T load1(const State &st, int k) const { return lv.template load1<T>(st, k); }
+    __device__ __forceinline__ uint2 unc_id(const State &st) const { return lv.unc_id(st); }
+    __device__ __forceinline__ State from_id(uint32_t x, uint32_t y) const { return lv.from_id(x, y); }
+};
+
 struct SinkEdgeFirst {
     int32_t *first; /* min invalid position per edge, TMK_FIRST_NONE = none so far */
     __device__ __forceinline__ void emit(const SrcEdgeLevel::State &st, size_t g, bool hit, int lane) const {
@@ -888,6 +913,57 @@ __global__ void k_edges_prep(const void *p0, const void *p1, int layout, size_t 
     nd[e] = n;
     first[e] = static_hit ? 0 : TMK_FIRST_NONE;
     if (n > max_nd) *overflow = 1u;
+}
+
+/* segment counts, first[] reset and the exclusive prefix sum of the counts for SrcEdgeFlat: one CTA, n_edge <= 4096 */
+__global__ void __launch_bounds__(1024) k_edges_prep_flat(const void *p0, const void *p1, int layout, size_t ld, int n_sub, uint32_t n_edge,
+                                                         double seg_len, int32_t *nd, int32_t *first, int static_hit, uint32_t *off) {
+    __shared__ uint32_t warp_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t mine[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t e = 4u * tid + k;
+        mine[k] = 0;
+        if (e < n_edge) {
+            double a[TMK_MAXSUB], b[TMK_MAXSUB];
+            for (int j = 0; j < n_sub; j++) {
+                a[j] = load_q<double>(p0, layout, ld, e, j);
+                b[j] = load_q<double>(p1, layout, ld, e, j);
+            }
+            const int n = segment_count(a, b, n_sub, seg_len);
+            nd[e] = n;
+            first[e] = static_hit ? 0 : TMK_FIRST_NONE;
+            mine[k] = (uint32_t)n; /* positions 0 .. nd-1: nd states */
+        }
+        sum += mine[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sum[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        warp_sum[lane] = wi - w; /* exclusive */
+    }
+    __syncthreads();
+    uint32_t run = warp_sum[warp] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t e = 4u * tid + k;
+        if (e < n_edge) off[e] = run;
+        run += mine[k];
+        if (e + 1 == n_edge) off[n_edge] = run;
+    }
 }
 
 /* survivors of level L that have states at level L+1 (nd > 2^L) */
