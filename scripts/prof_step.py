@@ -1,5 +1,5 @@
 """Profiling target: a few device-resident steps of one workload, nothing else (short enough for ncu --set full).
-usage: prof_step.py [configs|blocks|clutter|edges] [steps]"""
+usage: prof_step.py [configs|blocks|clutter|edges] [steps] [log2 of the batch size]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,6 +17,8 @@ cl = A.Collision(sg)
 sub = sg.config_indices(names)
 lim = W.arm_limit_table(names)
 n = 100_000 if wl == "edges" else 1 << 20
+if len(sys.argv) > 3:
+    n = 1 << int(sys.argv[3])
 s = torch.cuda.Stream()
 bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
 if wl == "edges":

@@ -1095,7 +1095,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
             if ((w >> 24) & 1) {
                 const SQuick &Q = sq[(w >> 8) & 0xffff];
                 ps4[k] = make_float4(Q.cx, Q.cy, Q.cz, Q.brad);
-            } else ps4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else ps4[k] = make_float4(0.f, 0.f, 0.f, mgf[(w >> 8) & 0xffff].brad); /* moving partner: its bounding radius (k_wave_fk) */
         }
         upload(im.ps4, ps4, cl->stream);
     }
@@ -1197,10 +1197,12 @@ static void launch_heavy(const Image<float> &f, const Src &src, const Sink &sink
     k_conv_items<Src, Sink><<<ctas, 128, 0, sc>>>(f, src, sink, u);
     CK(cudaGetLastError());
     if (fork) CK(cudaEventRecord(cl->ev_aux[1], sc));
-    static const bool simple = getenv("TMK_TRAVERSE_SIMPLE") != nullptr; /* A/B aid */
-    static const unsigned trav_ctas = getenv("TMK_TRAV_CTAS") ? (unsigned)atoi(getenv("TMK_TRAV_CTAS")) : 7u;
-    if (simple) k_mesh_traverse_simple<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
-    else k_mesh_traverse<Src, Sink><<<148 * trav_ctas, 128, 0, s>>>(f, src, sink, u, trav_next);
+    /* the tree walks: warp task stacks (default); TMK_TRAVERSE=pool / simple select the earlier kernels (A/B aid) */
+    static const int mode = !getenv("TMK_TRAVERSE") ? 0 : !strcmp(getenv("TMK_TRAVERSE"), "pool") ? 1 : !strcmp(getenv("TMK_TRAVERSE"), "simple") ? 2 : 0;
+    static const unsigned trav_ctas = getenv("TMK_TRAV_CTAS") ? (unsigned)atoi(getenv("TMK_TRAV_CTAS")) : (mode == 1 ? 7u : 6u);
+    if (mode == 2) k_mesh_traverse_simple<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
+    else if (mode == 1) k_mesh_traverse<Src, Sink><<<148 * trav_ctas, 128, 0, s>>>(f, src, sink, u, trav_next);
+    else k_mesh_tasks<Src, Sink><<<148 * trav_ctas, 128, 0, s>>>(f, src, sink, u, trav_next);
     CK(cudaGetLastError());
     k_tri_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
     CK(cudaGetLastError());
@@ -1298,7 +1300,7 @@ static size_t launch_wave(struct aa_rx_cl *cl, const void *dQ, int layout, size_
         k_wave_fk<SrcConfigs><<<gx, 256, smem, s>>>(im.f, src, w, u);
         k_wave_broad<<<dim3(gx, (unsigned)im.f.n_mg), 256, smem, s>>>(im.f, w, n, u, c0);
         k_wave_quick<<<148 * 8, 256, 0, s>>>(im.f, w, u, c0);
-        k_wave_export<<<148 * 4, 256, 0, s>>>(im.f, w, u, c0);
+        k_wave_export<<<148 * 16, 256, 0, s>>>(im.f, w, u, c0);
         k_wave_bits<<<gx, 256, 0, s>>>(w, n, d_bits + c0 / 32);
         CK(cudaGetLastError());
         launches += 5;

@@ -805,6 +805,157 @@ __global__ void __launch_bounds__(128) k_mesh_traverse(Image<float> im, Src src,
     }
 }
 
+/* The walks of 32 items at a time as two task stacks per warp.  A thread-per-item walk (and the pool above) is as
+ * slow as its longest item: a shape lying along the surface visits dozens of nodes and triangles, one dependent
+ * load after the other, while the lanes whose walk ended at the root box wait.  Here the warp keeps the queries of
+ * its 32 items in shared memory and works through a stack of (item, node) tasks and a stack of (item, triangle)
+ * tasks, 32 tasks per round whatever item they belong to: a round is one load latency, the number of rounds is the
+ * depth of the tree plus the work divided by 32, and every lane runs the same code (node rounds: box tests;
+ * triangle rounds: the per-triangle certificates).  Depth-first in batches (tasks are popped from the end), so the
+ * stacks stay short; an item that was hit drops its remaining tasks. */
+#define TMK_TASK_NQ 1024
+#define TMK_TASK_TQ 320
+#define TMK_TASK_F 22 /* floats of a query: Rms 9, tms 3, c 3, extents 3, rad2, shape a b c */
+template <class Src, class Sink>
+__global__ void __launch_bounds__(128) k_mesh_tasks(Image<float> im, Src src, Sink sink, UncList unc, uint32_t *next) {
+    __shared__ float s_f[4][TMK_TASK_F][32];
+    __shared__ uint32_t s_i[4][6][32]; /* shape kind, mesh record, node pointer (2 words), triangle pointer (2 words) */
+    __shared__ uint32_t s_nq[4][TMK_TASK_NQ];
+    __shared__ uint32_t s_tq[4][TMK_TASK_TQ];
+    __shared__ uint32_t s_dead[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float(*F)[32] = s_f[warp];
+    uint32_t(*I)[32] = s_i[warp];
+    uint32_t *nq = s_nq[warp], *tq = s_tq[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t n = *unc.mesh_n;
+    if (n > unc.mesh_cap) n = unc.mesh_cap;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) { base = atomicAdd(next, 32u); s_dead[warp] = 0u; }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + (uint32_t)lane;
+        bool has = false;
+        if (i < n) {
+            const HeavyRec h = heavy_load(unc.mesh_items + (size_t)i * TMK_MESH_REC);
+            const DGeom<float> &A = im.mg[ITEM_A(h.key)];
+            const DGeom<float> &B = ITEM_STATIC(h.key) ? im.sg[ITEM_B(h.key)] : im.mg[ITEM_B(h.key)];
+            const Xf<float> XB = ITEM_STATIC(h.key) ? xload(B.tf) : h.XB;
+            if (A.shape == K_MESH && B.shape == K_MESH) {
+                unc_emit(unc, h.id_x, h.id_y, h.key, TMK_WHOLE_PAIR); /* mesh against mesh: exact path only */
+            } else {
+                const bool a_mesh = A.shape == K_MESH;
+                const MeshRef<float> &M = im.meshes[a_mesh ? A.mesh : B.mesh];
+                const Shape<float> S = shape_of(a_mesh ? B : A);
+                MeshQuery<float> Q;
+                Q.init(a_mesh ? h.XA : XB, S, a_mesh ? XB : h.XA, a_mesh ? B.brad : A.brad);
+                F[0][lane] = Q.Rms.m00; F[1][lane] = Q.Rms.m01; F[2][lane] = Q.Rms.m02;
+                F[3][lane] = Q.Rms.m10; F[4][lane] = Q.Rms.m11; F[5][lane] = Q.Rms.m12;
+                F[6][lane] = Q.Rms.m20; F[7][lane] = Q.Rms.m21; F[8][lane] = Q.Rms.m22;
+                F[9][lane] = Q.tms.x; F[10][lane] = Q.tms.y; F[11][lane] = Q.tms.z;
+                F[12][lane] = Q.c.x; F[13][lane] = Q.c.y; F[14][lane] = Q.c.z;
+                F[15][lane] = Q.ex; F[16][lane] = Q.ey; F[17][lane] = Q.ez; F[18][lane] = Q.rad2;
+                F[19][lane] = S.a; F[20][lane] = S.b; F[21][lane] = S.c;
+                I[0][lane] = (uint32_t)S.kind; I[1][lane] = i;
+                const unsigned long long pn = (unsigned long long)(uintptr_t)M.nodes, pt = (unsigned long long)(uintptr_t)M.tris;
+                I[2][lane] = (uint32_t)pn; I[3][lane] = (uint32_t)(pn >> 32);
+                I[4][lane] = (uint32_t)pt; I[5][lane] = (uint32_t)(pt >> 32);
+                has = true;
+            }
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, has);
+        if (has) nq[__popc(hm & lt)] = (uint32_t)lane << 24; /* the root of every item */
+        int nq_n = __popc(hm), tq_n = 0;
+        bool overflow = false;
+        __syncwarp();
+        while (nq_n > 0 || tq_n > 0) {
+            const uint32_t dead = s_dead[warp];
+            if (tq_n >= 32 || nq_n == 0) { /* a round of triangles */
+                const int take = min(32, tq_n);
+                tq_n -= take;
+                if (lane < take) {
+                    const uint32_t t = tq[tq_n + lane];
+                    const int sl = (int)(t >> 24), tri = (int)(t & 0xffffffu);
+                    if (!((dead >> sl) & 1u)) {
+                        MeshQuery<float> Q;
+                        Q.Rms.m00 = F[0][sl]; Q.Rms.m01 = F[1][sl]; Q.Rms.m02 = F[2][sl];
+                        Q.Rms.m10 = F[3][sl]; Q.Rms.m11 = F[4][sl]; Q.Rms.m12 = F[5][sl];
+                        Q.Rms.m20 = F[6][sl]; Q.Rms.m21 = F[7][sl]; Q.Rms.m22 = F[8][sl];
+                        Q.tms = mk<float>(F[9][sl], F[10][sl], F[11][sl]);
+                        Shape<float> S;
+                        S.kind = (int)I[0][sl]; S.a = F[19][sl]; S.b = F[20][sl]; S.c = F[21][sl];
+                        const float *tris = (const float *)(uintptr_t)((unsigned long long)I[4][sl] | ((unsigned long long)I[5][sl] << 32));
+                        Vec3<float> p0, p1, p2;
+                        Q.tri_in_s(tris, tri, p0, p1, p2);
+                        int r;
+                        if (S.kind == K_SPHERE) r = test_tri_vs_shape(S, p0, p1, p2);
+                        else r = quick_tri(S, p0, p1, p2);
+                        if (r != SEP) {
+                            const uint32_t rec = I[1][sl];
+                            if (r == NEED) { /* open triangle: to the triangle list (GJK in k_tri_items) */
+                                const uint32_t k = atomicAdd(unc.tri_n, 1u);
+                                if (k < unc.tri_cap) unc.tri_items[k] = make_uint2(rec, (uint32_t)tri);
+                                else r = UNC;
+                            }
+                            if (r == HIT || r == UNC) {
+                                const float4 r0 = unc.mesh_items[(size_t)rec * TMK_MESH_REC];
+                                if (r == HIT) {
+                                    sink.mark_hit(src.from_id(__float_as_uint(r0.x), __float_as_uint(r0.y)));
+                                    atomicOr(&s_dead[warp], 1u << sl);
+                                } else unc_emit(unc, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z), (uint32_t)tri);
+                            }
+                        }
+                    }
+                }
+            } else { /* a round of nodes */
+                const int take = min(32, nq_n);
+                nq_n -= take;
+                int ca = 0, cb = 0, sl = 0; /* what this lane pushes: two children (cb < 0) or cb triangles from ca on */
+                if (lane < take) {
+                    const uint32_t t = nq[nq_n + lane];
+                    sl = (int)(t >> 24);
+                    if (!((dead >> sl) & 1u)) {
+                        const BvhNode *nodes = (const BvhNode *)(uintptr_t)((unsigned long long)I[2][sl] | ((unsigned long long)I[3][sl] << 32));
+                        const BvhNode nd = load_node(nodes, (int)(t & 0xffffffu));
+                        MeshQuery<float> Q;
+                        Q.c = mk<float>(F[12][sl], F[13][sl], F[14][sl]);
+                        Q.ex = F[15][sl]; Q.ey = F[16][sl]; Q.ez = F[17][sl]; Q.rad2 = F[18][sl];
+                        if (Q.overlaps(nd)) { ca = nd.a; cb = nd.b; }
+                    }
+                }
+                __syncwarp(); /* the popped entries were read: the slots may be overwritten */
+                const unsigned inner = __ballot_sync(0xffffffffu, cb < 0);
+                const int ntri = cb > 0 ? cb : 0;
+                int incl = ntri;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int tri_total = __shfl_sync(0xffffffffu, incl, 31);
+                if (nq_n + 2 * __popc(inner) > TMK_TASK_NQ || tq_n + tri_total > TMK_TASK_TQ) { overflow = true; break; }
+                if (cb < 0) {
+                    const int o = nq_n + 2 * __popc(inner & lt);
+                    nq[o] = ((uint32_t)sl << 24) | (uint32_t)ca;
+                    nq[o + 1] = ((uint32_t)sl << 24) | (uint32_t)(-cb - 1);
+                }
+                for (int j = 0; j < ntri; j++) tq[tq_n + incl - ntri + j] = ((uint32_t)sl << 24) | (uint32_t)(ca + j);
+                nq_n += 2 * __popc(inner);
+                tq_n += tri_total;
+            }
+            __syncwarp();
+        }
+        if (overflow) { /* cannot happen for the trees the host builds: every item not yet hit goes to the exact path */
+            if (has && !((s_dead[warp] >> lane) & 1u)) {
+                const float4 r0 = unc.mesh_items[(size_t)i * TMK_MESH_REC];
+                unc_emit(unc, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z), TMK_WHOLE_PAIR);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 /* both lists in one launch, triangles decided inline: for the swept-edge levels, whose lists are short
  * and whose launch count matters more than warp convergence */
 template <class Src, class Sink>

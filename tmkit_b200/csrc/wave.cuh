@@ -74,17 +74,27 @@ struct WaveStage {
             if (pass) put(w, unc, base + __popc(m & ((1u << lane) - 1u)), s, a, b, b_static);
         }
     }
-    __device__ __forceinline__ void flush(const WaveBuf &w, const UncList &unc, int lane) const {
-        __syncwarp();
-        const uint32_t nst = min(*cnt, (uint32_t)TMK_WAVE_STAGE);
-        if (nst) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&w.counters[0], nst);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (uint32_t i = lane; i < nst; i += 32) {
-                if (base + i < w.queue_cap) w.queue[base + i] = stage[i];
+    /* CTA-wide flush (every thread of the CTA calls it; `stage`/`cnt` of warp 0 must be passed as stage0/cnt0): one
+     * global atomic per CTA - the queue counter is a single address every CTA of the launch appends to */
+    __device__ __forceinline__ static void flush_cta(const WaveBuf &w, const UncList &unc, const uint2 *stage0, const uint32_t *cnt0,
+                                                     uint32_t *s_base, int tid) {
+        __syncthreads();
+        uint32_t fill[8], total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { fill[k] = min(cnt0[k], (uint32_t)TMK_WAVE_STAGE); total += fill[k]; }
+        if (total == 0) return; /* CTA-uniform */
+        if (tid == 0) *s_base = atomicAdd(&w.counters[0], total);
+        __syncthreads();
+        const uint32_t base = *s_base;
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint2 *src = stage0 + (size_t)k * TMK_WAVE_STAGE;
+            for (uint32_t i = tid; i < fill[k]; i += 256) {
+                if (base + run + i < w.queue_cap) w.queue[base + run + i] = src[i];
                 else *unc.overflow = 1u;
             }
+            run += fill[k];
         }
     }
 };
@@ -96,6 +106,7 @@ template <class Src>
 __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveBuf w, UncList unc) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t cnt[8];
+    __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WaveStage ws;
     ws.stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE;
@@ -128,21 +139,44 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
             const Vec3<float> ca = bound_centre(A, XA);
             gx[a] = ca.x; gy[a] = ca.y; gz[a] = ca.z;
             const float ra = A.brad + pad;
-            for (int p = im.pa_begin[3 * a + 2]; p < im.pa_begin[3 * a + 3]; p++) { /* moving partners */
-                const int b = (im.t_pairs[p] >> 8) & 0xffff;
+            /* moving partners: the partner's bounding radius rides in ps4[p].w; four pairs per vote (most groups
+             * have no survivor in any lane), their loads issued together */
+            const uint32_t *PAIRS = im.t_pairs;
+            const float4 *PS4 = (const float4 *)im.ps4;
+            int p = im.pa_begin[3 * a + 2];
+            const int pe = im.pa_begin[3 * a + 3];
+            for (; p + 4 <= pe; p += 4) {
+                int b[4];
+                bool pass[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) b[u] = (int)((PAIRS[p + u] >> 8) & 0xffff);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float dx = gx[b[u]] - ca.x, dy = gy[b[u]] - ca.y, dz = gz[b[u]] - ca.z;
+                    const float reach = ra + PS4[p + u].w;
+                    pass[u] = live && dx * dx + dy * dy + dz * dz <= reach * reach;
+                }
+                if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) ws.vote(w, unc, pass[u], s, a, b[u], 0, lane);
+                }
+            }
+            for (; p < pe; p++) {
+                const int b = (int)((PAIRS[p] >> 8) & 0xffff);
                 const float dx = gx[b] - ca.x, dy = gy[b] - ca.y, dz = gz[b] - ca.z;
-                const float reach = ra + im.mg[b].brad;
+                const float reach = ra + PS4[p].w;
                 ws.vote(w, unc, live && dx * dx + dy * dy + dz * dz <= reach * reach, s, a, b, 0, lane);
             }
         }
     }
-    ws.flush(w, unc, lane);
+    WaveStage::flush_cta(w, unc, (const uint2 *)smem, cnt, &s_base, tid);
 }
 
 /* broadphase of moving geometry a = blockIdx.y against its partner lists and the static grid */
 __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, uint32_t n, UncList unc, size_t id_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t cnt[8];
+    __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StaticGrid &G = im.grid;
     uint2 *stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE; /* 8 warps x TMK_WAVE_STAGE survivors */
@@ -236,7 +270,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
             }
         }
     }
-    ws.flush(w, unc, lane);
+    WaveStage::flush_cta(w, unc, (const uint2 *)smem, cnt, &s_base, tid);
     (void)id_base;
 }
 
