@@ -64,15 +64,17 @@ struct WaveStage {
             else *unc.overflow = 1u;
         }
     }
-    /* warp-uniform call: every lane votes, passing lanes get consecutive slots */
-    __device__ __forceinline__ void vote(const WaveBuf &w, const UncList &unc, bool pass, uint32_t s, int a, int b, int b_static, int lane) const {
+    /* warp-uniform call: every lane votes, passing lanes get consecutive slots.  The warp's fill is a warp-uniform
+     * register (every lane adds the same popc): no atomic, no shuffle; publish() stores it for the flush */
+    uint32_t fill;
+    __device__ __forceinline__ void vote(const WaveBuf &w, const UncList &unc, bool pass, uint32_t s, int a, int b, int b_static, int lane) {
         const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(cnt, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) put(w, unc, base + __popc(m & ((1u << lane) - 1u)), s, a, b, b_static);
-        }
+        if (pass) put(w, unc, fill + __popc(m & ((1u << lane) - 1u)), s, a, b, b_static);
+        fill += __popc(m);
+    }
+    __device__ __forceinline__ void publish(int lane) const {
+        if (lane == 0) *cnt = fill;
+        __syncwarp();
     }
     /* CTA-wide flush (every thread of the CTA calls it; `stage`/`cnt` of warp 0 must be passed as stage0/cnt0): one
      * global atomic per CTA - the queue counter is a single address every CTA of the launch appends to */
@@ -111,8 +113,7 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
     WaveStage ws;
     ws.stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE;
     ws.cnt = &cnt[warp];
-    if (lane == 0) cnt[warp] = 0;
-    __syncwarp();
+    ws.fill = 0;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const typename Src::State st = src.prepare(s);
     const bool live = st.live && !im.static_hit;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
             }
         }
     }
+    ws.publish(lane);
     WaveStage::flush_cta(w, unc, (const uint2 *)smem, cnt, &s_base, tid);
 }
 
@@ -180,8 +182,6 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StaticGrid &G = im.grid;
     uint2 *stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE; /* 8 warps x TMK_WAVE_STAGE survivors */
-    if (lane == 0) cnt[warp] = 0;
-    __syncthreads();
 
     const int a = blockIdx.y;
     const uint32_t s = blockIdx.x * 256u + tid;
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     WaveStage ws;
     ws.stage = stage;
     ws.cnt = &cnt[warp];
+    ws.fill = 0;
     auto enqueue = [&](int p, bool pass) { /* warp-uniform call */
         const uint32_t wd = PAIRS[p];
         ws.vote(w, unc, pass, s, a, (int)((wd >> 8) & 0xffff), (int)((wd >> 24) & 1), lane);
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     }
     for (; p < e1; p++) enqueue(p, box_pass(p));
     (void)e2; /* the moving partners were voted on by k_wave_fk */
+    ws.publish(lane); /* the grid walk below appends lane by lane, through the shared counter */
     if (G.r_on && live) { /* one run of candidates: everything a geometry centred in this cell could touch */
         const float fx = (ca.x - G.r_ox) * G.r_inv_h, fy = (ca.y - G.r_oy) * G.r_inv_h, fz = (ca.z - G.r_oz) * G.r_inv_h;
         const int ix = (int)floorf(fx), iy = (int)floorf(fy), iz = (int)floorf(fz);
