@@ -1090,12 +1090,21 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     }
     {
         std::vector<float4> ps4(tpairs.size() + 1);
+        /* .w = (bounding radius of the owner + the kernels' pad + bounding radius of the partner)^2, rounded up: the
+         * sphere tests of the broadphase compare a squared distance with it (static partners: centre in .xyz) */
+        auto reach2 = [](double ra, double rb) {
+            const double r = ra + 4.0 * 1.0e-5 + rb, r2 = r * r;
+            float f = (float)r2;
+            if ((double)f < r2) f = nextafterf(f, INFINITY);
+            return f;
+        };
         for (size_t k = 0; k < tpairs.size(); k++) {
             uint32_t w = tpairs[k].w;
+            const double ra = (double)mgf[tpairs[k].owner].brad;
             if ((w >> 24) & 1) {
                 const SQuick &Q = sq[(w >> 8) & 0xffff];
-                ps4[k] = make_float4(Q.cx, Q.cy, Q.cz, Q.brad);
-            } else ps4[k] = make_float4(0.f, 0.f, 0.f, mgf[(w >> 8) & 0xffff].brad); /* moving partner: its bounding radius (k_wave_fk) */
+                ps4[k] = make_float4(Q.cx, Q.cy, Q.cz, reach2(ra, (double)Q.brad));
+            } else ps4[k] = make_float4(0.f, 0.f, 0.f, reach2(ra, (double)mgf[(w >> 8) & 0xffff].brad));
         }
         upload(im.ps4, ps4, cl->stream);
     }

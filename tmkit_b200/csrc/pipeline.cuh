@@ -470,8 +470,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                         for (int u = 0; u < 4; u++) {
                             const float4 c4 = PS4[p + u];
                             const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-                            const float reach = ra + c4.w;
-                            pass[u] = live && dx * dx + dy * dy + dz * dz <= reach * reach;
+                            pass[u] = live && dx * dx + dy * dy + dz * dz <= c4.w; /* .w = (ra + pad + rb)^2 */
                         }
                         if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
 #pragma unroll
@@ -481,8 +480,7 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                     for (; p < e0; p++) {
                         const float4 c4 = PS4[p];
                         const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-                        const float reach = ra + c4.w;
-                        enqueue(p, live && dx * dx + dy * dy + dz * dz <= reach * reach);
+                        enqueue(p, live && dx * dx + dy * dy + dz * dz <= c4.w);
                     }
                     /* static boxes: bounding sphere of A against the box itself (exact point-box distance) */
                     auto box_pass = [&](int pp) {

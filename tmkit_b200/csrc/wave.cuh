@@ -81,22 +81,23 @@ struct WaveStage {
     __device__ __forceinline__ static void flush_cta(const WaveBuf &w, const UncList &unc, const uint2 *stage0, const uint32_t *cnt0,
                                                      uint32_t *s_base, int tid) {
         __syncthreads();
-        uint32_t fill[8], total = 0;
+        const int warp = tid >> 5, lane = tid & 31;
+        uint32_t total = 0, before = 0, mine = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) { fill[k] = min(cnt0[k], (uint32_t)TMK_WAVE_STAGE); total += fill[k]; }
+        for (int k = 0; k < 8; k++) {
+            const uint32_t f = min(cnt0[k], (uint32_t)TMK_WAVE_STAGE);
+            if (k < warp) before += f;
+            if (k == warp) mine = f;
+            total += f;
+        }
         if (total == 0) return; /* CTA-uniform */
         if (tid == 0) *s_base = atomicAdd(&w.counters[0], total);
         __syncthreads();
-        const uint32_t base = *s_base;
-        uint32_t run = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint2 *src = stage0 + (size_t)k * TMK_WAVE_STAGE;
-            for (uint32_t i = tid; i < fill[k]; i += 256) {
-                if (base + run + i < w.queue_cap) w.queue[base + run + i] = src[i];
-                else *unc.overflow = 1u;
-            }
-            run += fill[k];
+        const uint32_t base = *s_base + before; /* every warp copies its own region */
+        const uint2 *src = stage0 + (size_t)warp * TMK_WAVE_STAGE;
+        for (uint32_t i = lane; i < mine; i += 32) {
+            if (base + i < w.queue_cap) w.queue[base + i] = src[i];
+            else *unc.overflow = 1u;
         }
     }
 };
@@ -139,7 +140,6 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
             }
             const Vec3<float> ca = bound_centre(A, XA);
             gx[a] = ca.x; gy[a] = ca.y; gz[a] = ca.z;
-            const float ra = A.brad + pad;
             /* moving partners: the partner's bounding radius rides in ps4[p].w; four pairs per vote (most groups
              * have no survivor in any lane), their loads issued together */
             const uint32_t *PAIRS = im.t_pairs;
@@ -154,8 +154,7 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const float dx = gx[b[u]] - ca.x, dy = gy[b[u]] - ca.y, dz = gz[b[u]] - ca.z;
-                    const float reach = ra + PS4[p + u].w;
-                    pass[u] = live && dx * dx + dy * dy + dz * dz <= reach * reach;
+                    pass[u] = live && dx * dx + dy * dy + dz * dz <= PS4[p + u].w; /* .w = (ra + pad + rb)^2 */
                 }
                 if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
 #pragma unroll
@@ -165,8 +164,7 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
             for (; p < pe; p++) {
                 const int b = (int)((PAIRS[p] >> 8) & 0xffff);
                 const float dx = gx[b] - ca.x, dy = gy[b] - ca.y, dz = gz[b] - ca.z;
-                const float reach = ra + PS4[p].w;
-                ws.vote(w, unc, live && dx * dx + dy * dy + dz * dz <= reach * reach, s, a, b, 0, lane);
+                ws.vote(w, unc, live && dx * dx + dy * dy + dz * dz <= PS4[p].w, s, a, b, 0, lane);
             }
         }
     }
@@ -192,7 +190,8 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     const float *oa = w.pose + (size_t)a * 7 * cap + sc;
     Vec3<float> ca = mk<float>(oa[4 * cap], oa[5 * cap], oa[6 * cap]);
     if (A.shape == K_MESH) ca = bound_centre(A, wave_pose(w, a, sc));
-    const float ra = A.brad + Num<float>::eps() * 4.0f;
+    if (!live) ca = mk<float>(1.0e18f, 1.0e18f, 1.0e18f); /* no test passes: squared distances ~ 1e36, no overflow */
+    const float ra = A.brad + Num<float>::eps() * 4.0f, ra2 = ra * ra;
     const uint32_t *PAIRS = im.t_pairs;
     const float4 *PS4 = (const float4 *)im.ps4;
     const SQuick *SQ = (const SQuick *)im.sq;
@@ -215,8 +214,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
         for (int u = 0; u < 4; u++) {
             const float4 c4 = PS4[p + u];
             const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-            const float reach = ra + c4.w;
-            pass[u] = live && dx * dx + dy * dy + dz * dz <= reach * reach;
+            pass[u] = dx * dx + dy * dy + dz * dz <= c4.w; /* .w = (ra + pad + rb)^2; a dead lane's centre is far away */
         }
         if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
 #pragma unroll
@@ -226,8 +224,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     for (; p < e0; p++) {
         const float4 c4 = PS4[p];
         const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-        const float reach = ra + c4.w;
-        enqueue(p, live && dx * dx + dy * dy + dz * dz <= reach * reach);
+        enqueue(p, dx * dx + dy * dy + dz * dz <= c4.w);
     }
     /* static boxes / mesh boxes: bounding sphere of A against the box itself (exact point-box distance) */
     auto box_pass = [&](int pp) {
@@ -240,7 +237,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
         const float ex = fmaxf(fabsf(dx * x4.x + dy * x4.y + dz * x4.z) - x4.w, 0.f);
         const float ey = fmaxf(fabsf(dx * y4.x + dy * y4.y + dz * y4.z) - y4.w, 0.f);
         const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
-        return live && ex * ex + ey * ey + ez * ez <= ra * ra;
+        return ex * ex + ey * ey + ez * ez <= ra2;
     };
     for (; p + 2 <= e1; p += 2) {
         const bool p0 = box_pass(p), p1 = box_pass(p + 1);
