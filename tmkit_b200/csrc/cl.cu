@@ -1288,7 +1288,7 @@ static WaveBuf wave_buffers(struct aa_rx_cl *cl, size_t n_states) {
     w.hit = (uint8_t *)cl->d_whit.p;
     w.queue = (uint2 *)cl->d_wqueue.p;
     w.pend = (uint2 *)cl->d_wpend.p;
-    w.counters = nullptr; /* set by the caller: words 16, 17 of the batch's counter block */
+    w.qcnt = w.pcnt = nullptr; /* set by the caller: words 16 .. 25 of the batch's counter block */
     return w;
 }
 /* states [begin, end) of the batch at dQ through the wavefront kernels; exported items join the batch's lists */
@@ -1296,23 +1296,38 @@ static size_t launch_wave(struct aa_rx_cl *cl, const void *dQ, int layout, size_
                           uint32_t *d_bits, const UncList &u, cudaStream_t s) {
     ImageDev &im = cl->img;
     WaveBuf w = wave_buffers(cl, end - begin);
-    w.counters = u.n + 16;
+    w.pcnt = u.n + 16;
     const size_t smem = sizeof(uint2) * 8 * TMK_WAVE_STAGE;
     size_t launches = 0;
+    /* the broadphase and the quick certificates in stages over the moving geometries, deepest first: a state a stage
+     * condemns is skipped by the later ones (both kernels test the state's flag first) */
+    const int n_mg = im.f.n_mg;
+    static const int want = getenv("TMK_WAVE_STAGES") ? atoi(getenv("TMK_WAVE_STAGES")) : 0; /* tuning aid */
+    const int n_stage = std::max(1, std::min(std::min(8, n_mg), want > 0 ? want : (n_mg >= 16 ? 3 : n_mg >= 6 ? 2 : 1)));
+    static const bool shallow = getenv("TMK_WAVE_ORDER") && !strcmp(getenv("TMK_WAVE_ORDER"), "shallow"); /* A/B aid */
     for (size_t c0 = begin; c0 < end; c0 += TMK_WAVE_CHUNK) {
         const size_t c1 = std::min(end, c0 + TMK_WAVE_CHUNK);
         const uint32_t n = (uint32_t)(c1 - c0);
         SrcConfigs src;
         src.p = dQ; src.layout = layout; src.ld = ld; src.n = n; src.s_begin = c0;
-        CK(cudaMemsetAsync(w.counters, 0, 8, s));
+        CK(cudaMemsetAsync(u.n + 16, 0, 40, s)); /* pend fill and the queue fills of up to eight stages */
         const unsigned gx = (n + 255) / 256;
+        w.qcnt = u.n + 18;
         k_wave_fk<SrcConfigs><<<gx, 256, smem, s>>>(im.f, src, w, u);
-        k_wave_broad<<<dim3(gx, (unsigned)im.f.n_mg), 256, smem, s>>>(im.f, w, n, u, c0);
-        k_wave_quick<<<148 * 8, 256, 0, s>>>(im.f, w, u, c0);
+        launches++;
+        for (int g = 0; g < n_stage; g++) {
+            /* index ranges, the highest first: geometries are listed in chain order, the deep ones sweep the most space */
+            const int gg = shallow ? g : n_stage - 1 - g;
+            const int a0 = (int)((long)n_mg * gg / n_stage), a1 = (int)((long)n_mg * (gg + 1) / n_stage);
+            w.qcnt = u.n + 18 + g; /* the moving-moving pairs k_wave_fk voted on ride with stage 0 */
+            k_wave_broad<<<dim3(gx, (unsigned)(a1 - a0)), 256, smem, s>>>(im.f, w, n, u, c0, a0);
+            k_wave_quick<<<148 * 8, 256, 0, s>>>(im.f, w, u, c0);
+            launches += 2;
+        }
         k_wave_export<<<148 * 16, 256, 0, s>>>(im.f, w, u, c0);
         k_wave_bits<<<gx, 256, 0, s>>>(w, n, d_bits + c0 / 32);
         CK(cudaGetLastError());
-        launches += 5;
+        launches += 2;
     }
     return launches;
 }

@@ -37,7 +37,8 @@ struct WaveBuf {
     uint8_t *hit;       /* [cap] 1 = the state is known to collide */
     uint2 *queue;       /* broadphase survivors: (state in the chunk, pair key = ITEM_KEY layout) */
     uint2 *pend;        /* pairs the quick certificates left open */
-    uint32_t *counters; /* [0] queue fill, [1] pend fill */
+    uint32_t *qcnt;     /* queue fill of the stage in flight */
+    uint32_t *pcnt;     /* pend fill (all stages of the chunk) */
     uint32_t cap;       /* states per chunk */
     uint32_t queue_cap, pend_cap;
 };
@@ -59,7 +60,7 @@ struct WaveStage {
         const uint2 item = make_uint2(s, ITEM_KEY(item_pack(0, a, b, b_static)));
         if (idx < TMK_WAVE_STAGE) stage[idx] = item;
         else { /* the warp's staging area is full: straight to the queue */
-            const uint32_t k = atomicAdd(&w.counters[0], 1u);
+            const uint32_t k = atomicAdd(w.qcnt, 1u);
             if (k < w.queue_cap) w.queue[k] = item;
             else *unc.overflow = 1u;
         }
@@ -91,7 +92,7 @@ struct WaveStage {
             total += f;
         }
         if (total == 0) return; /* CTA-uniform */
-        if (tid == 0) *s_base = atomicAdd(&w.counters[0], total);
+        if (tid == 0) *s_base = atomicAdd(w.qcnt, total);
         __syncthreads();
         const uint32_t base = *s_base + before; /* every warp copies its own region */
         const uint2 *src = stage0 + (size_t)warp * TMK_WAVE_STAGE;
@@ -173,7 +174,9 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
 }
 
 /* broadphase of moving geometry a = blockIdx.y against its partner lists and the static grid */
-__global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, uint32_t n, UncList unc, size_t id_base) {
+/* a0: first geometry of the stage (blockIdx.y counts from it; the index stays in the uniform datapath - read from a
+ * table it would not, and every partner-list load of the kernel would turn into per-lane address arithmetic: +15 %) */
+__global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, uint32_t n, UncList unc, size_t id_base, int a0) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t cnt[8];
     __shared__ uint32_t s_base;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     const StaticGrid &G = im.grid;
     uint2 *stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE; /* 8 warps x TMK_WAVE_STAGE survivors */
 
-    const int a = blockIdx.y;
+    const int a = a0 + (int)blockIdx.y;
     const uint32_t s = blockIdx.x * 256u + tid;
     const bool live = s < n && w.hit[s] == 0;
     const DGeom<float> &A = im.mg[a];
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
 
 /* quick certificates for the broadphase survivors */
 __global__ void __launch_bounds__(256) k_wave_quick(Image<float> im, WaveBuf w, UncList unc, size_t id_base) {
-    uint32_t n = w.counters[0];
+    uint32_t n = *w.qcnt;
     if (n > w.queue_cap) n = w.queue_cap;
     const SQuick *SQ = (const SQuick *)im.sq;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(256) k_wave_quick(Image<float> im, WaveBuf w, 
         else if (r == NEED) {
             const auto g = cooperative_groups::coalesced_threads(); /* one atomic per warp, not per item */
             uint32_t k = 0;
-            if (g.thread_rank() == 0) k = atomicAdd(&w.counters[1], (uint32_t)g.size());
+            if (g.thread_rank() == 0) k = atomicAdd(w.pcnt, (uint32_t)g.size());
             k = g.shfl(k, 0) + g.thread_rank();
             if (k < w.pend_cap) w.pend[k] = it;
             else unc_emit(unc, (uint32_t)(id_base + s), 0u, key, TMK_WHOLE_PAIR);
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(256) k_wave_quick(Image<float> im, WaveBuf w, 
 
 /* records for the deferred narrowphase, only for states no certificate has condemned yet */
 __global__ void __launch_bounds__(256) k_wave_export(Image<float> im, WaveBuf w, UncList unc, size_t id_base) {
-    uint32_t n = w.counters[1];
+    uint32_t n = *w.pcnt;
     if (n > w.pend_cap) n = w.pend_cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint2 it = w.pend[i];
