@@ -1977,7 +1977,14 @@ static FkImage *fk_image(const struct aa_rx_sg *sg, size_t n_sub, const aa_rx_co
         const double *src = slot[f] >= 0 ? &fold[7 * (size_t)f] : &ab[7 * (size_t)f];
         for (int i = 0; i < 7; i++) outs[k].tf[i] = (float)src[i];
         outs[k].slot = slot[f];
+        outs[k].out = (int)k;
     }
+    /* the kernel writes a joint's frames while its pose is in registers: table sorted by slot (constants first);
+     * joints whose children do not follow them directly are the only ones it keeps in its per-thread array */
+    std::stable_sort(outs.begin(), outs.end(), [](const FkOut &x, const FkOut &y) { return x.slot < y.slot; });
+    for (size_t j = 0; j < joints.size(); j++) joints[j].pad = 0;
+    for (size_t j = 0; j < joints.size(); j++)
+        if (joints[j].parent >= 0 && joints[j].parent != (int)j - 1) joints[joints[j].parent].pad = 1;
     CK(cudaDeviceSynchronize()); /* launches in flight may still read the old tables */
     upload(im->joints, joints, 0);
     upload(im->outs, outs, 0);

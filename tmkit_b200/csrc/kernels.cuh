@@ -317,6 +317,8 @@ __global__ void k_fk_single64(const DFrame *fr, int n_f, const double *q, double
 struct FkOut {
     float tf[7]; /* slot >= 0: pose relative to that joint | slot < 0: the constant world pose */
     int slot;
+    int out;     /* position in the caller's frame list (the table is sorted by slot: a joint's frames are written while
+                  * its pose is still in registers) */
 };
 #define TMK_TF_ROWS_F64 0
 #define TMK_TF_SOA_F32 1
@@ -332,26 +334,33 @@ __global__ void __launch_bounds__(256) k_fk_frames(const DJoint<float> *joints, 
     __syncthreads();
     const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (c >= n_cfg) return;
-    Xf<float> jp[TMK_MAXJ];
-    for (int j = 0; j < n_joint; j++) {
-        const DJoint<float> &Jt = J[j];
-        Xf<float> par;
-        if (Jt.parent >= 0) par = jp[Jt.parent];
-        jp[j] = fk_joint(xload(Jt.E), mk<float>(Jt.ax[0], Jt.ax[1], Jt.ax[2]), Jt.off, Jt.type, load_q<float>(Q, layout, ld, c, Jt.qslot),
-                         Jt.parent >= 0 ? &par : (const Xf<float> *)nullptr);
-    }
-    for (int k = 0; k < n_out; k++) {
-        const FkOut &o = O[k];
-        Xf<float> X = xload(o.tf);
-        if (o.slot >= 0) X = xmul(jp[o.slot], X);
+    auto store = [&](int out, const Xf<float> &X) {
         if (TF_LAYOUT == TMK_TF_SOA_F32) {
-            float *p = (float *)TF + (size_t)k * 7 * ld_tf + c;
+            float *p = (float *)TF + (size_t)out * 7 * ld_tf + c;
             p[0] = X.r.x; p[ld_tf] = X.r.y; p[2 * ld_tf] = X.r.z; p[3 * ld_tf] = X.r.w;
             p[4 * ld_tf] = X.v.x; p[5 * ld_tf] = X.v.y; p[6 * ld_tf] = X.v.z;
         } else {
-            double *p = (double *)TF + (c * (size_t)n_out + (size_t)k) * 7;
+            double *p = (double *)TF + (c * (size_t)n_out + (size_t)out) * 7;
             p[0] = X.r.x; p[1] = X.r.y; p[2] = X.r.z; p[3] = X.r.w; p[4] = X.v.x; p[5] = X.v.y; p[6] = X.v.z;
         }
+    };
+    int k = 0;
+    for (; k < n_out && O[k].slot < 0; k++) store(O[k].out, xload(O[k].tf)); /* frames no varied joint moves */
+    /* The chain runs in registers: a joint's pose is the parent of the next one in a serial chain, and its frames are
+     * written at once.  Only joints with a child that does not follow them directly (pad != 0) are kept in the
+     * per-thread array - a dynamically indexed array lives in local memory, and with every joint in it the kernel moved
+     * more local-memory bytes than poses (round 2: 54 % -> see profiles/README.md). */
+    Xf<float> jp[TMK_MAXJ];
+    Xf<float> cur;
+    cur.r.x = cur.r.y = cur.r.z = 0.f; cur.r.w = 1.f; cur.v = mk<float>(0.f, 0.f, 0.f);
+    for (int j = 0; j < n_joint; j++) {
+        const DJoint<float> &Jt = J[j];
+        Xf<float> par = cur;
+        if (Jt.parent >= 0 && Jt.parent != j - 1) par = jp[Jt.parent];
+        cur = fk_joint(xload(Jt.E), mk<float>(Jt.ax[0], Jt.ax[1], Jt.ax[2]), Jt.off, Jt.type, load_q<float>(Q, layout, ld, c, Jt.qslot),
+                       Jt.parent >= 0 ? &par : (const Xf<float> *)nullptr);
+        if (Jt.pad) jp[j] = cur;
+        for (; k < n_out && O[k].slot == j; k++) store(O[k].out, xmul(cur, xload(O[k].tf)));
     }
 }
 
