@@ -24,16 +24,24 @@ if [[ $ST == *l* ]]; then
   done
 fi
 if [[ $ST == *f* ]]; then
-  for WL in configs clutter; do
-    CMD="python bench.py --steps 2 --warmup 3 --no-cpu --workload $WL"
-    timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_wave' -s 15 -c 5 \
-      -f -o $O/${T}_${WL}_prof $CMD > $O/${T}_${WL}_ncu_full.log 2>&1; echo "full $WL rc $?"
-  done
-  CMD="python bench.py --steps 2 --warmup 3 --no-cpu --workload edges"
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_states_tile -s 6 -c 1 \
-    -f -o $O/${T}_edges_prof $CMD > $O/${T}_edges_ncu_full.log 2>&1; echo "full edges rc $?"
+  # full captures: prof_step.py runs three ungraphed steps of one workload (the kernels are the bench's)
+  cap() { # <name> <workload> <kernel regex> <skip> <count>
+    TMK_NO_GRAPH=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$3" -s $4 -c $5 \
+      -f -o $O/${T}_$1 python scripts/prof_step.py $2 3 > $O/${T}_$1_ncu.log 2>&1; echo "full $1 rc $?"
+    : > $O/${T}_$1_ncu_summary.txt
+    for ((i = 0; i < $5; i++)); do python scripts/ncu_summary.py $O/${T}_$1.ncu-rep $i 0 2>&1 | grep -v "^instruction share\|^ *[0-9.]*%" >> $O/${T}_$1_ncu_summary.txt; echo >> $O/${T}_$1_ncu_summary.txt; done
+    ncu -i $O/${T}_$1.ncu-rep --page raw --csv > $O/${T}_$1_raw.csv 2>/dev/null
+  }
+  cap configs_main configs 'k_wave_fk|k_wave_export|k_wave_bits' 3 3
+  cap configs_broad configs 'k_wave_broad|k_wave_quick' 4 4
+  cap configs_tail configs 'k_conv_items|k_mesh_tasks|k_tri_items|k_recheck_items' 4 4
+  cap clutter clutter 'k_wave_fk|k_wave_broad|k_wave_quick' 0 3
+  cap edges edges 'k_states_tile' 14 1
+  cap edges_heavy edges 'k_heavy_mixed' 4 1
+  for K in k_wave_broad k_wave_quick; do python scripts/ncu_lines.py $O/${T}_configs_broad.ncu-rep $K 14 > $O/${T}_lines_$K.txt 2>&1; done
+  for K in k_wave_fk; do python scripts/ncu_lines.py $O/${T}_configs_main.ncu-rep $K 14 > $O/${T}_lines_$K.txt 2>&1; done
+  for K in k_mesh_tasks k_tri_items; do python scripts/ncu_lines.py $O/${T}_configs_tail.ncu-rep $K 14 > $O/${T}_lines_$K.txt 2>&1; done
+  python scripts/ncu_lines.py $O/${T}_edges.ncu-rep k_states_tile 14 > $O/${T}_lines_k_states_tile.txt 2>&1
+  rm -f $O/${T}_clutter.ncu-rep $O/${T}_edges.ncu-rep $O/${T}_edges_heavy.ncu-rep
 fi
-for R in $O/${T}_*_prof.ncu-rep; do
-  ncu -i $R --page raw --csv > ${R%.ncu-rep}_raw.csv 2>/dev/null
-done
-du -sm $O; ls -la $O | tail -n 30
+du -sm $O; ls -la $O | tail -n 40

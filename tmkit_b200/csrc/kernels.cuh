@@ -186,17 +186,20 @@ __device__ __forceinline__ void fk_config(const Image<T> &im, const T *q, Xf<T> 
  * later of their joints - parents precede children in the joint table - and no other geometry pose is built */
 template <typename T>
 __device__ __forceinline__ void fk_pair(const Image<T> &im, const T *q, int a, int b, Xf<T> &XA, Xf<T> &XB) {
-    Xf<T> jp[TMK_MAXJ];
+    Xf<T> jp[TMK_MAXJ]; /* only joints with a child that does not follow them directly land here (local memory) */
     const int sa = im.mg[a].slot, sb = b >= 0 ? im.mg[b].slot : -1;
     const int last = sa > sb ? sa : sb;
+    Xf<T> cur;
+    cur.r.x = cur.r.y = cur.r.z = T(0); cur.r.w = T(1); cur.v = mk<T>(T(0), T(0), T(0));
     for (int j = 0; j <= last; j++) {
         const DJoint<T> &J = im.joints[j];
-        Xf<T> par;
-        if (J.parent >= 0) par = jp[J.parent];
-        jp[j] = fk_joint(xload(J.E), mk<T>(J.ax[0], J.ax[1], J.ax[2]), J.off, J.type, q[J.qslot], J.parent >= 0 ? &par : nullptr);
+        Xf<T> par = cur;
+        if (J.parent >= 0 && J.parent != j - 1) par = jp[J.parent];
+        cur = fk_joint(xload(J.E), mk<T>(J.ax[0], J.ax[1], J.ax[2]), J.off, J.type, q[J.qslot], J.parent >= 0 ? &par : nullptr);
+        if (J.pad) jp[j] = cur;
+        if (j == sa) XA = xmul(cur, xload(im.mg[a].tf));
+        if (j == sb) XB = xmul(cur, xload(im.mg[b].tf));
     }
-    XA = xmul(jp[sa], xload(im.mg[a].tf));
-    if (b >= 0) XB = xmul(jp[sb], xload(im.mg[b].tf));
 }
 
 /* validity of one configuration: SEP (free), HIT, UNC.  pairhit != NULL: no early-out, colliding
