@@ -343,11 +343,13 @@ def test_kernel_variants_agree(gpu_sussman, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"TMK_QCAP": "4"}, {"TMK_QCAP": "4", "TMK_SPILL_CAP": "0"},
-                                 {"TMK_QCAP": "4", "TMK_SPILL_CAP": "16", "TMK_UNC_CAP": "64"}, {"TMK_UNC_CAP": "1"}])
+                                 {"TMK_QCAP": "4", "TMK_SPILL_CAP": "16", "TMK_UNC_CAP": "64"}, {"TMK_UNC_CAP": "1"},
+                                 {"TMK_TASK_CAP": "32"}])
 def test_overflow_paths_keep_verdicts(gpu_sussman, monkeypatch, env):
     """full shared-memory queues spill into global memory, a full spill area hands pairs to the exact
-    (double) re-check, and a full undecided list triggers the brute-force double kernel: slower, same
-    bits - configurations and edges."""
+    (double) re-check, a full undecided list triggers the brute-force double kernel, and full task stacks of the
+    tree-walk kernel (k_mesh_tasks) hand their items to the exact re-check: slower, same bits - configurations
+    and edges."""
     sc, orc, sg, cl, q0 = gpu_sussman
     sub = sg.config_indices(S.RIGHT_ARM)
     lim = W.arm_limit_table(S.RIGHT_ARM)
@@ -536,6 +538,12 @@ def test_wavefront_pipeline_equals_the_tile_kernel(monkeypatch):
     orc = _oracle_scene(sc, q0)
     st, _ = orc.check_batch(orc.config_ids(names), q0, Q[:3000], threads=CORES, early_out=True)
     _assert_verdicts(got["wave"][:3000], st, "wavefront pipeline")
+    # the broadphase / quick-certificate stages (a condemned state skips the later ones): any stage count, same bits
+    for stages in ("1", "2", "5"):
+        monkeypatch.setenv("TMK_WAVE_STAGES", stages)
+        sg_s, cl_s, _ = _gpu_scene(sc, q0)
+        assert np.array_equal(cl_s.check_batch(sub, q0, Q[:300_000]), got["wave"][:300_000]), stages
+    monkeypatch.delenv("TMK_WAVE_STAGES")
     # queues too small for the survivors: the overflow flag sends every state through the exact kernel
     monkeypatch.setenv("TMK_WAVE_QCAP", "500")
     assert np.array_equal(cl.check_batch(sub, q0, Q[:6000]), got["wave"][:6000])

@@ -1252,6 +1252,8 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     u.tri_items = (uint2 *)b_tri.p;
     u.tri_n = (uint32_t *)b_cnt.p + 6;
     u.tile_ctr = (uint32_t *)b_cnt.p + 26; /* words 26, 27 */
+    u.task_cap = TMK_TASK_NQ;
+    if (const char *e = getenv("TMK_TASK_CAP")) u.task_cap = (uint32_t)std::max(32, atoi(e)); /* test aid: the overflow path of k_mesh_tasks */
     if (reset) CK(cudaMemsetAsync(b_cnt.p, 0, 512, s)); /* after every allocation: capturable */
     return u;
 }
@@ -1302,7 +1304,7 @@ static size_t launch_wave(struct aa_rx_cl *cl, const void *dQ, int layout, size_
     /* the broadphase and the quick certificates in stages over the moving geometries, deepest first: a state a stage
      * condemns is skipped by the later ones (both kernels test the state's flag first) */
     const int n_mg = im.f.n_mg;
-    static const int want = getenv("TMK_WAVE_STAGES") ? atoi(getenv("TMK_WAVE_STAGES")) : 0; /* tuning aid */
+    const int want = getenv("TMK_WAVE_STAGES") ? atoi(getenv("TMK_WAVE_STAGES")) : 0; /* tuning / test aid (read per call) */
     const int n_stage = std::max(1, std::min(std::min(8, n_mg), want > 0 ? want : (n_mg >= 16 ? 3 : n_mg >= 6 ? 2 : 1)));
     static const bool shallow = getenv("TMK_WAVE_ORDER") && !strcmp(getenv("TMK_WAVE_ORDER"), "shallow"); /* A/B aid */
     for (size_t c0 = begin; c0 < end; c0 += TMK_WAVE_CHUNK) {

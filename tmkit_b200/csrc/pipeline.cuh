@@ -100,6 +100,7 @@ struct UncList {
     uint32_t *tri_n;
     uint32_t tri_cap;
     uint32_t *tile_ctr; /* [0] next tile of the running k_states_tile launch, [1] CTAs that finished it */
+    uint32_t task_cap;  /* k_mesh_tasks: entries of a warp's task stacks it may use (<= TMK_TASK_TQ; test aid, forces the overflow path) */
 };
 #define TMK_MESH_REC 5 /* float4 per exported mesh item: (id_x, id_y, key, -) poseA[7] - poseB[7] - */
 #define TMK_WHOLE_PAIR 0xffffffffu
@@ -828,6 +829,7 @@ __global__ void __launch_bounds__(128) k_mesh_tasks(Image<float> im, Src src, Si
     const unsigned lt = (1u << lane) - 1u;
     uint32_t n = *unc.mesh_n;
     if (n > unc.mesh_cap) n = unc.mesh_cap;
+    const int nq_cap = (int)min(unc.task_cap, (uint32_t)TMK_TASK_NQ), tq_cap = (int)min(unc.task_cap, (uint32_t)TMK_TASK_TQ);
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) { base = atomicAdd(next, 32u); s_dead[warp] = 0u; }
@@ -932,7 +934,7 @@ __global__ void __launch_bounds__(128) k_mesh_tasks(Image<float> im, Src src, Si
                     if (lane >= d) incl += v;
                 }
                 const int tri_total = __shfl_sync(0xffffffffu, incl, 31);
-                if (nq_n + 2 * __popc(inner) > TMK_TASK_NQ || tq_n + tri_total > TMK_TASK_TQ) { overflow = true; break; }
+                if (nq_n + 2 * __popc(inner) > nq_cap || tq_n + tri_total > tq_cap) { overflow = true; break; }
                 if (cb < 0) {
                     const int o = nq_n + 2 * __popc(inner & lt);
                     nq[o] = ((uint32_t)sl << 24) | (uint32_t)ca;
