@@ -389,7 +389,7 @@ extern "C" void tmk_mesh_compiled_release(void *compiled) { delete (HostMesh *)c
 
 /* ------------------------------------------------------------------ the collision context */
 struct ImageDev {
-    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, g_cells, g_items, g_live, g_c4, g_rstart, g_rc, g_rid;
+    DBuf jf, jd, mgf, mgd, sgf, sgd, pairs, sq, jg, pa, ps4, tpairs, tkeys, ab4, paabb, g_cells, g_items, g_live, g_c4, g_rstart, g_rc, g_rid;
     Image<float> f;
     Image<double> d;
     std::vector<uint32_t> h_pairs;
@@ -587,7 +587,7 @@ extern "C" void aa_rx_cl_destroy(struct aa_rx_cl *cl) {
     DBuf *bufs[] = {&cl->d_geoms, &cl->d_nodes, &cl->d_trisf, &cl->d_trisd, &cl->d_meshf, &cl->d_meshd, &cl->d_gpairs,
                     &cl->d_gout, &cl->d_tf, &cl->d_spill, &cl->d_mesh, &cl->d_conv, &cl->d_tri, &cl->d_wpose, &cl->d_whit, &cl->d_wqueue, &cl->d_wpend, &cl->d_q, &cl->d_q1, &cl->d_bits, &cl->d_unc, &cl->d_cnt, &cl->d_first,
                     &cl->d_pairhit, &cl->d_stats, &cl->d_nd, &cl->d_alive0, &cl->d_alive1, &cl->d_efirst, &cl->img.jf, &cl->img.jd, &cl->img.mgf, &cl->img.mgd, &cl->img.sgf,
-                    &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4, &cl->img.tpairs, &cl->img.g_cells, &cl->img.g_items,
+                    &cl->img.sgd, &cl->img.pairs, &cl->img.sq, &cl->img.jg, &cl->img.pa, &cl->img.ps4, &cl->img.tpairs, &cl->img.tkeys, &cl->img.ab4, &cl->img.paabb, &cl->img.g_cells, &cl->img.g_items,
                     &cl->img.g_live, &cl->img.g_c4, &cl->img.g_rstart, &cl->img.g_rc, &cl->img.g_rid};
     for (DBuf *b : bufs) b->release();
     for (cudaEvent_t e : cl->ev_pool) cudaEventDestroy(e);
@@ -835,7 +835,7 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         return dist > reach * (1 + 1e-9) + 1e-4;
     };
 
-    struct P { uint32_t w; int fa, fb, owner, seg; };
+    struct P { uint32_t w; int fa, fb, owner, seg, aligned; };
     std::vector<P> pairs;
     for (size_t a = 0; a < cl->n_g; a++) {
         if (g2m[a] < 0) continue;
@@ -854,12 +854,26 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
              * large flat boxes and mesh boxes; a small box is as well served by its bounding sphere */
             const bool big_box = (cl->geoms[b].shape == TMK_BOX && cl->geoms[b].brad > 0.2) || cl->geoms[b].shape == TMK_MESH;
             p.seg = g2m[b] >= 0 ? 2 : (big_box ? 1 : 0);
+            /* a box segment entry whose box is aligned with the world axes (tables, walls): the wavefront broadphase
+             * tests those as centre + half extents; they come first in the segment */
+            p.aligned = 0;
+            if (p.seg == 1) {
+                const double *t = sgv[g2s[b]].tf;
+                const double x = t[0], y = t[1], z = t[2], ww = t[3];
+                const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * ww), 2 * (x * z + y * ww),
+                                     2 * (x * y + z * ww), 1 - 2 * (x * x + z * z), 2 * (y * z - x * ww),
+                                     2 * (x * z - y * ww), 2 * (y * z + x * ww), 1 - 2 * (x * x + y * y)};
+                p.aligned = 1;
+                for (double r : R)
+                    if (!(fabs(r) < 1e-9 || fabs(r) > 1 - 1e-9)) p.aligned = 0;
+            }
             pairs.push_back(p);
         }
     }
     std::stable_sort(pairs.begin(), pairs.end(), [](const P &x, const P &y) {
         if (x.owner != y.owner) return x.owner < y.owner;
         if (x.seg != y.seg) return x.seg < y.seg;
+        if (x.aligned != y.aligned) return x.aligned > y.aligned;
         return (x.w >> 28) < (y.w >> 28);
     });
     im.h_pairs.clear(); im.pair_fa.clear(); im.pair_fb.clear();
@@ -1045,6 +1059,28 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
         }
     }
 
+    /* wavefront broadphase tables in t_pairs order: ready queue keys, world-aligned boxes, end of the aligned part */
+    std::vector<uint32_t> t_keys(tpairs.size() + 1, 0u);
+    std::vector<float4> ab4(2 * tpairs.size() + 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int> pa_aabb(mg.size() + 1, 0);
+    for (size_t a = 0; a < mg.size(); a++) pa_aabb[a] = pa_begin[3 * a + 1];
+    for (size_t k = 0; k < tpairs.size(); k++) {
+        const uint32_t w = tpairs[k].w;
+        const int b = (int)((w >> 8) & 0xffff), st = (int)((w >> 24) & 1);
+        t_keys[k] = ((uint32_t)tpairs[k].owner << 17) | ((uint32_t)st << 16) | (uint32_t)b; /* ITEM_KEY(item_pack(0, a, b, st)) */
+        if (tpairs[k].seg == 1 && tpairs[k].aligned) {
+            const SQuick &Q = sq[b];
+            const float R[9] = {Q.a0x, Q.a1x, Q.a2x, Q.a0y, Q.a1y, Q.a2y, Q.a0z, Q.a1z, Q.a2z}; /* row i: world component i of the axes */
+            float h[3];
+            for (int i = 0; i < 3; i++) {
+                const double e = fabs((double)R[3 * i]) * Q.h0 + fabs((double)R[3 * i + 1]) * Q.h1 + fabs((double)R[3 * i + 2]) * Q.h2;
+                h[i] = nextafterf((float)(e * (1 + 1e-6)), INFINITY); /* outward: the test stays conservative */
+            }
+            ab4[2 * k] = make_float4(Q.cx, Q.cy, Q.cz, 0.f);
+            ab4[2 * k + 1] = make_float4(h[0], h[1], h[2], 0.f);
+            pa_aabb[tpairs[k].owner] = (int)k + 1;
+        }
+    }
     hs.mark("host lists");
     /* hoisted static-static pairs, evaluated once (double) */
     std::vector<uint2> sp;
@@ -1076,6 +1112,9 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     upload(im.jg, jg_begin, cl->stream);
     upload(im.pa, pa_begin, cl->stream);
     upload(im.tpairs, h_tpairs, cl->stream);
+    upload(im.tkeys, t_keys, cl->stream);
+    upload(im.ab4, ab4, cl->stream);
+    upload(im.paabb, pa_aabb, cl->stream);
     upload(im.g_cells, cell_start, cl->stream);
     upload(im.g_items, cell_items, cl->stream);
     upload(im.g_live, live_ms, cl->stream);
@@ -1127,6 +1166,9 @@ static void ensure_image(struct aa_rx_cl *cl, size_t n_sub, const aa_rx_config_i
     im.d.pa_begin = im.f.pa_begin = (const int *)im.pa.p;
     im.d.ps4 = im.f.ps4 = im.ps4.p;
     im.d.t_pairs = im.f.t_pairs = (const uint32_t *)im.tpairs.p;
+    im.d.t_keys = im.f.t_keys = (const uint32_t *)im.tkeys.p;
+    im.d.ab4 = im.f.ab4 = im.ab4.p;
+    im.d.pa_aabb = im.f.pa_aabb = (const int *)im.paabb.p;
     im.d.n_tpair = im.f.n_tpair = (int)h_tpairs.size();
     grid.cell_start = (const int *)im.g_cells.p;
     grid.items = (const unsigned short *)im.g_items.p;

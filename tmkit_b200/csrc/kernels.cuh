@@ -83,6 +83,9 @@ template <typename T> struct Image {
                           * tested by bounding sphere [3a], static boxes [3a+1], moving partners [3a+2] .. [3a+3] */
     const void *ps4;     /* float4[n_tpair]: bounding centre + radius of the static partner, in t_pairs order */
     const uint32_t *t_pairs; /* the pipeline's pair list: `pairs` minus the pairs the grid covers (same array without a grid) */
+    const uint32_t *t_keys;  /* [n_tpair] the queue key of every pair (ITEM_KEY layout), ready to store (wave.cuh) */
+    const void *ab4;         /* float4[2 * n_tpair]: world-aligned boxes of the box segment - centre, half extents (wave.cuh) */
+    const int *pa_aabb;      /* [n_mg] end of the axis-aligned part of geometry a's box segment (pairs sorted: aligned first) */
     int n_tpair;
     StaticGrid grid;
     int n_joint, n_mg, n_sg, n_pair;

@@ -57,7 +57,10 @@ struct WaveStage {
     uint2 *stage;      /* this warp's TMK_WAVE_STAGE slots */
     uint32_t *cnt;     /* this warp's fill */
     __device__ __forceinline__ void put(const WaveBuf &w, const UncList &unc, uint32_t idx, uint32_t s, int a, int b, int b_static) const {
-        const uint2 item = make_uint2(s, ITEM_KEY(item_pack(0, a, b, b_static)));
+        put_key(w, unc, idx, s, ITEM_KEY(item_pack(0, a, b, b_static)));
+    }
+    __device__ __forceinline__ void put_key(const WaveBuf &w, const UncList &unc, uint32_t idx, uint32_t s, uint32_t key) const {
+        const uint2 item = make_uint2(s, key);
         if (idx < TMK_WAVE_STAGE) stage[idx] = item;
         else { /* the warp's staging area is full: straight to the queue */
             const uint32_t k = atomicAdd(w.qcnt, 1u);
@@ -73,6 +76,12 @@ struct WaveStage {
         if (pass) put(w, unc, fill + __popc(m & ((1u << lane) - 1u)), s, a, b, b_static);
         fill += __popc(m);
     }
+    /* the same with the pair's queue key ready (Image::t_keys) */
+    __device__ __forceinline__ void vote_key(const WaveBuf &w, const UncList &unc, bool pass, uint32_t s, uint32_t key, int lane) {
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (pass) put_key(w, unc, fill + __popc(m & ((1u << lane) - 1u)), s, key);
+        fill += __popc(m);
+    }
     __device__ __forceinline__ void publish(int lane) const {
         if (lane == 0) *cnt = fill;
         __syncwarp();
@@ -83,14 +92,15 @@ struct WaveStage {
                                                      uint32_t *s_base, int tid) {
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
-        uint32_t total = 0, before = 0, mine = 0;
+        /* fills of the eight warps: lane k holds warp k's, a shuffle scan gives the total and this warp's offset */
+        uint32_t f = lane < 8 ? min(cnt0[lane], (uint32_t)TMK_WAVE_STAGE) : 0u, incl = f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t f = min(cnt0[k], (uint32_t)TMK_WAVE_STAGE);
-            if (k < warp) before += f;
-            if (k == warp) mine = f;
-            total += f;
+        for (int d = 1; d < 8; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
         }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
+        const uint32_t mine = __shfl_sync(0xffffffffu, f, warp), before = __shfl_sync(0xffffffffu, incl, warp) - mine;
         if (total == 0) return; /* CTA-uniform */
         if (tid == 0) *s_base = atomicAdd(w.qcnt, total);
         __syncthreads();
@@ -165,13 +175,13 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
                 }
                 if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) ws.vote(w, unc, pass[u], s, a, b[u], 0, lane);
+                    for (int u = 0; u < 4; u++) ws.vote_key(w, unc, pass[u], s, im.t_keys[p + u], lane);
                 }
             }
             for (; p < pe; p++) {
                 const int b = (int)((PAIRS[p] >> 8) & 0xffff);
                 const float dx = gx[b] - ca.x, dy = gy[b] - ca.y, dz = gz[b] - ca.z;
-                ws.vote(w, unc, live && dx * dx + dy * dy + dz * dz <= PS4[p].w, s, a, b, 0, lane);
+                ws.vote_key(w, unc, live && dx * dx + dy * dy + dz * dz <= PS4[p].w, s, im.t_keys[p], lane);
             }
         }
     }
@@ -210,10 +220,8 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
     ws.stage = stage;
     ws.cnt = &cnt[warp];
     ws.fill = 0;
-    auto enqueue = [&](int p, bool pass) { /* warp-uniform call */
-        const uint32_t wd = PAIRS[p];
-        ws.vote(w, unc, pass, s, a, (int)((wd >> 8) & 0xffff), (int)((wd >> 24) & 1), lane);
-    };
+    const uint32_t *KEYS = im.t_keys;
+    auto enqueue = [&](int p, bool pass) { ws.vote_key(w, unc, pass, s, KEYS[p], lane); }; /* warp-uniform call */
     int p = PA[3 * a];
     const int e0 = PA[3 * a + 1], e1 = PA[3 * a + 2], e2 = PA[3 * a + 3];
     /* static partners by bounding sphere: four tests, one vote (most groups have no survivor in any lane) */
@@ -248,6 +256,25 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
         const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
         return ex * ex + ey * ey + ez * ez <= ra2;
     };
+    /* the world-aligned boxes of the segment first (tables, walls, most mesh boxes): centre and half extents, no axes */
+    const float4 *AB4 = (const float4 *)im.ab4;
+    auto aabb_pass = [&](int pp) {
+        const float4 c4 = AB4[2 * pp], h4 = AB4[2 * pp + 1];
+        const float ex = fmaxf(fabsf(c4.x - ca.x) - h4.x, 0.f), ey = fmaxf(fabsf(c4.y - ca.y) - h4.y, 0.f),
+                    ez = fmaxf(fabsf(c4.z - ca.z) - h4.z, 0.f);
+        return ex * ex + ey * ey + ez * ez <= ra2;
+    };
+    const int e0a = im.pa_aabb[a];
+    for (; p + 4 <= e0a; p += 4) {
+        bool pass[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) pass[u] = aabb_pass(p + u);
+        if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) enqueue(p + u, pass[u]);
+        }
+    }
+    for (; p < e0a; p++) enqueue(p, aabb_pass(p));
     for (; p + 2 <= e1; p += 2) {
         const bool p0 = box_pass(p), p1 = box_pass(p + 1);
         if (__any_sync(0xffffffffu, p0 | p1)) { enqueue(p, p0); enqueue(p + 1, p1); }
