@@ -927,20 +927,30 @@ __global__ void __launch_bounds__(128) k_mesh_tasks(Image<float> im, Src src, Si
                 __syncwarp(); /* the popped entries were read: the slots may be overwritten */
                 const unsigned inner = __ballot_sync(0xffffffffu, cb < 0);
                 const int ntri = cb > 0 ? cb : 0;
-                int incl = ntri;
+                /* slots of this lane's triangles: the host's trees have leaves of one or two triangles - two ballots;
+                 * larger leaves take the shuffle scan */
+                const unsigned m1 = __ballot_sync(0xffffffffu, ntri >= 1), m2 = __ballot_sync(0xffffffffu, ntri >= 2);
+                int excl = __popc(m1 & lt) + __popc(m2 & lt), tri_total = __popc(m1) + __popc(m2);
+                if (__any_sync(0xffffffffu, ntri > 2)) {
+                    int incl = ntri;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    tri_total = __shfl_sync(0xffffffffu, incl, 31);
+                    excl = incl - ntri;
                 }
-                const int tri_total = __shfl_sync(0xffffffffu, incl, 31);
                 if (nq_n + 2 * __popc(inner) > nq_cap || tq_n + tri_total > tq_cap) { overflow = true; break; }
                 if (cb < 0) {
                     const int o = nq_n + 2 * __popc(inner & lt);
                     nq[o] = ((uint32_t)sl << 24) | (uint32_t)ca;
                     nq[o + 1] = ((uint32_t)sl << 24) | (uint32_t)(-cb - 1);
                 }
-                for (int j = 0; j < ntri; j++) tq[tq_n + incl - ntri + j] = ((uint32_t)sl << 24) | (uint32_t)(ca + j);
+                const uint32_t t0 = ((uint32_t)sl << 24) | (uint32_t)ca;
+                if (ntri >= 1) tq[tq_n + excl] = t0;
+                if (ntri >= 2) tq[tq_n + excl + 1] = t0 + 1u;
+                for (int j = 2; j < ntri; j++) tq[tq_n + excl + j] = t0 + (uint32_t)j;
                 nq_n += 2 * __popc(inner);
                 tq_n += tri_total;
             }
