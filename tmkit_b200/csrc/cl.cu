@@ -1364,7 +1364,10 @@ static size_t launch_wave(struct aa_rx_cl *cl, const void *dQ, int layout, size_
             const int gg = shallow ? g : n_stage - 1 - g;
             const int a0 = (int)((long)n_mg * gg / n_stage), a1 = (int)((long)n_mg * (gg + 1) / n_stage);
             w.qcnt = u.n + 18 + g; /* the moving-moving pairs k_wave_fk voted on ride with stage 0 */
-            k_wave_broad<<<dim3(gx, (unsigned)(a1 - a0)), 256, smem, s>>>(im.f, w, n, u, c0, a0);
+            /* two states per thread: measured 0.674 -> 0.633 ms per 2^20 (three or four: 64 registers, slower) */
+            static const int broad_k = getenv("TMK_BROAD_K") ? atoi(getenv("TMK_BROAD_K")) : 2; /* A/B aid */
+            if (broad_k == 2) k_wave_broad<2><<<dim3((n + 511) / 512, (unsigned)(a1 - a0)), 256, smem, s>>>(im.f, w, n, u, c0, a0);
+            else k_wave_broad<1><<<dim3(gx, (unsigned)(a1 - a0)), 256, smem, s>>>(im.f, w, n, u, c0, a0);
             k_wave_quick<<<148 * 8, 256, 0, s>>>(im.f, w, u, c0);
             launches += 2;
         }

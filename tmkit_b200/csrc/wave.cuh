@@ -54,14 +54,15 @@ __device__ __forceinline__ Xf<float> wave_pose(const WaveBuf &w, int g, uint32_t
 
 /* warp-level staging of broadphase survivors: appended in shared memory, flushed to the queue with one atomic */
 struct WaveStage {
-    uint2 *stage;      /* this warp's TMK_WAVE_STAGE slots */
+    uint2 *stage;      /* this warp's slots */
+    uint32_t cap = TMK_WAVE_STAGE; /* ... how many */
     uint32_t *cnt;     /* this warp's fill */
     __device__ __forceinline__ void put(const WaveBuf &w, const UncList &unc, uint32_t idx, uint32_t s, int a, int b, int b_static) const {
         put_key(w, unc, idx, s, ITEM_KEY(item_pack(0, a, b, b_static)));
     }
     __device__ __forceinline__ void put_key(const WaveBuf &w, const UncList &unc, uint32_t idx, uint32_t s, uint32_t key) const {
         const uint2 item = make_uint2(s, key);
-        if (idx < TMK_WAVE_STAGE) stage[idx] = item;
+        if (idx < cap) stage[idx] = item;
         else { /* the warp's staging area is full: straight to the queue */
             const uint32_t k = atomicAdd(w.qcnt, 1u);
             if (k < w.queue_cap) w.queue[k] = item;
@@ -89,11 +90,11 @@ struct WaveStage {
     /* CTA-wide flush (every thread of the CTA calls it; `stage`/`cnt` of warp 0 must be passed as stage0/cnt0): one
      * global atomic per CTA - the queue counter is a single address every CTA of the launch appends to */
     __device__ __forceinline__ static void flush_cta(const WaveBuf &w, const UncList &unc, const uint2 *stage0, const uint32_t *cnt0,
-                                                     uint32_t *s_base, int tid) {
+                                                     uint32_t *s_base, int tid, uint32_t stage_cap = TMK_WAVE_STAGE) {
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
         /* fills of the eight warps: lane k holds warp k's, a shuffle scan gives the total and this warp's offset */
-        uint32_t f = lane < 8 ? min(cnt0[lane], (uint32_t)TMK_WAVE_STAGE) : 0u, incl = f;
+        uint32_t f = lane < 8 ? min(cnt0[lane], stage_cap) : 0u, incl = f;
 #pragma unroll
         for (int d = 1; d < 8; d <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
@@ -105,7 +106,7 @@ struct WaveStage {
         if (tid == 0) *s_base = atomicAdd(w.qcnt, total);
         __syncthreads();
         const uint32_t base = *s_base + before; /* every warp copies its own region */
-        const uint2 *src = stage0 + (size_t)warp * TMK_WAVE_STAGE;
+        const uint2 *src = stage0 + (size_t)warp * stage_cap;
         for (uint32_t i = lane; i < mine; i += 32) {
             if (base + i < w.queue_cap) w.queue[base + i] = src[i];
             else *unc.overflow = 1u;
@@ -189,27 +190,37 @@ __global__ void __launch_bounds__(256) k_wave_fk(Image<float> im, Src src, WaveB
     WaveStage::flush_cta(w, unc, (const uint2 *)smem, cnt, &s_base, tid);
 }
 
-/* broadphase of moving geometry a = blockIdx.y against its partner lists and the static grid */
-/* a0: first geometry of the stage (blockIdx.y counts from it; the index stays in the uniform datapath - read from a
- * table it would not, and every partner-list load of the kernel would turn into per-lane address arithmetic: +15 %) */
+/* broadphase of moving geometry a = a0 + blockIdx.y against its partner lists and the static grid.
+ * a0: first geometry of the stage (the index stays in the uniform datapath - read from a table it would not, and
+ * every partner-list load of the kernel would hang off a local-memory load: +15 %).
+ * K states per thread (s, s + 256, ...): the partner data, the loop and its address arithmetic are shared by the K
+ * tests of a pair. */
+template <int K>
 __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, uint32_t n, UncList unc, size_t id_base, int a0) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t cnt[8];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StaticGrid &G = im.grid;
-    uint2 *stage = (uint2 *)smem + (size_t)warp * TMK_WAVE_STAGE; /* 8 warps x TMK_WAVE_STAGE survivors */
+    constexpr uint32_t STAGE = K > 2 ? 2 * TMK_WAVE_STAGE : TMK_WAVE_STAGE; /* survivors staged per warp */
+    uint2 *stage = (uint2 *)smem + (size_t)warp * STAGE;
 
     const int a = a0 + (int)blockIdx.y;
-    const uint32_t s = blockIdx.x * 256u + tid;
-    const bool live = s < n && w.hit[s] == 0;
     const DGeom<float> &A = im.mg[a];
-    const uint32_t sc = s < n ? s : 0;
     const size_t cap = w.cap;
-    const float *oa = w.pose + (size_t)a * 7 * cap + sc;
-    Vec3<float> ca = mk<float>(oa[4 * cap], oa[5 * cap], oa[6 * cap]);
-    if (A.shape == K_MESH) ca = bound_centre(A, wave_pose(w, a, sc));
-    if (!live) ca = mk<float>(1.0e18f, 1.0e18f, 1.0e18f); /* no test passes: squared distances ~ 1e36, no overflow */
+    uint32_t s[K];
+    bool live[K];
+    Vec3<float> ca[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        s[k] = blockIdx.x * (256u * K) + 256u * k + tid;
+        live[k] = s[k] < n && w.hit[s[k]] == 0;
+        const uint32_t sc = s[k] < n ? s[k] : 0;
+        const float *oa = w.pose + (size_t)a * 7 * cap + sc;
+        ca[k] = mk<float>(oa[4 * cap], oa[5 * cap], oa[6 * cap]);
+        if (A.shape == K_MESH) ca[k] = bound_centre(A, wave_pose(w, a, sc));
+        if (!live[k]) ca[k] = mk<float>(1.0e18f, 1.0e18f, 1.0e18f); /* no test passes: squared distances ~ 1e36, no overflow */
+    }
     const float ra = A.brad + Num<float>::eps() * 4.0f, ra2 = ra * ra;
     const uint32_t *PAIRS = im.t_pairs;
     const float4 *PS4 = (const float4 *)im.ps4;
@@ -218,94 +229,134 @@ __global__ void __launch_bounds__(256) k_wave_broad(Image<float> im, WaveBuf w, 
 
     WaveStage ws;
     ws.stage = stage;
+    ws.cap = STAGE;
     ws.cnt = &cnt[warp];
     ws.fill = 0;
     const uint32_t *KEYS = im.t_keys;
-    auto enqueue = [&](int p, bool pass) { ws.vote_key(w, unc, pass, s, KEYS[p], lane); }; /* warp-uniform call */
+    auto enqueue = [&](int p, const bool (&pass)[K]) { /* warp-uniform call */
+        const uint32_t key = KEYS[p];
+#pragma unroll
+        for (int k = 0; k < K; k++) ws.vote_key(w, unc, pass[k], s[k], key, lane);
+    };
     int p = PA[3 * a];
     const int e0 = PA[3 * a + 1], e1 = PA[3 * a + 2], e2 = PA[3 * a + 3];
     /* static partners by bounding sphere: four tests, one vote (most groups have no survivor in any lane) */
     for (; p + 4 <= e0; p += 4) {
-        bool pass[4];
+        bool pass[4][K];
+        bool any = false;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const float4 c4 = PS4[p + u];
-            const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-            pass[u] = dx * dx + dy * dy + dz * dz <= c4.w; /* .w = (ra + pad + rb)^2; a dead lane's centre is far away */
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const float dx = c4.x - ca[k].x, dy = c4.y - ca[k].y, dz = c4.z - ca[k].z;
+                pass[u][k] = dx * dx + dy * dy + dz * dz <= c4.w; /* .w = (ra + pad + rb)^2; a dead lane's centre is far away */
+                any |= pass[u][k];
+            }
         }
-        if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
+        if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
             for (int u = 0; u < 4; u++) enqueue(p + u, pass[u]);
         }
     }
     for (; p < e0; p++) {
         const float4 c4 = PS4[p];
-        const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-        enqueue(p, dx * dx + dy * dy + dz * dz <= c4.w);
+        bool pass[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const float dx = c4.x - ca[k].x, dy = c4.y - ca[k].y, dz = c4.z - ca[k].z;
+            pass[k] = dx * dx + dy * dy + dz * dz <= c4.w;
+        }
+        enqueue(p, pass);
     }
     /* static boxes / mesh boxes: bounding sphere of A against the box itself (exact point-box distance) */
-    auto box_pass = [&](int pp) {
+    auto box_pass = [&](int pp, bool (&pass)[K]) {
         const int b = (PAIRS[pp] >> 8) & 0xffff;
         const float4 c4 = *reinterpret_cast<const float4 *>(&SQ[b].cx);
         const float4 x4 = *reinterpret_cast<const float4 *>(&SQ[b].a0x);
         const float4 y4 = *reinterpret_cast<const float4 *>(&SQ[b].a1x);
         const float4 z4 = *reinterpret_cast<const float4 *>(&SQ[b].a2x);
-        const float dx = c4.x - ca.x, dy = c4.y - ca.y, dz = c4.z - ca.z;
-        const float ex = fmaxf(fabsf(dx * x4.x + dy * x4.y + dz * x4.z) - x4.w, 0.f);
-        const float ey = fmaxf(fabsf(dx * y4.x + dy * y4.y + dz * y4.z) - y4.w, 0.f);
-        const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
-        return ex * ex + ey * ey + ez * ez <= ra2;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const float dx = c4.x - ca[k].x, dy = c4.y - ca[k].y, dz = c4.z - ca[k].z;
+            const float ex = fmaxf(fabsf(dx * x4.x + dy * x4.y + dz * x4.z) - x4.w, 0.f);
+            const float ey = fmaxf(fabsf(dx * y4.x + dy * y4.y + dz * y4.z) - y4.w, 0.f);
+            const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
+            pass[k] = ex * ex + ey * ey + ez * ez <= ra2;
+            any |= pass[k];
+        }
+        return any;
     };
     /* the world-aligned boxes of the segment first (tables, walls, most mesh boxes): centre and half extents, no axes */
     const float4 *AB4 = (const float4 *)im.ab4;
-    auto aabb_pass = [&](int pp) {
+    auto aabb_pass = [&](int pp, bool (&pass)[K]) {
         const float4 c4 = AB4[2 * pp], h4 = AB4[2 * pp + 1];
-        const float ex = fmaxf(fabsf(c4.x - ca.x) - h4.x, 0.f), ey = fmaxf(fabsf(c4.y - ca.y) - h4.y, 0.f),
-                    ez = fmaxf(fabsf(c4.z - ca.z) - h4.z, 0.f);
-        return ex * ex + ey * ey + ez * ez <= ra2;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const float ex = fmaxf(fabsf(c4.x - ca[k].x) - h4.x, 0.f), ey = fmaxf(fabsf(c4.y - ca[k].y) - h4.y, 0.f),
+                        ez = fmaxf(fabsf(c4.z - ca[k].z) - h4.z, 0.f);
+            pass[k] = ex * ex + ey * ey + ez * ez <= ra2;
+            any |= pass[k];
+        }
+        return any;
     };
     const int e0a = im.pa_aabb[a];
     for (; p + 4 <= e0a; p += 4) {
-        bool pass[4];
+        bool pass[4][K];
+        bool any = false;
 #pragma unroll
-        for (int u = 0; u < 4; u++) pass[u] = aabb_pass(p + u);
-        if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
+        for (int u = 0; u < 4; u++) any |= aabb_pass(p + u, pass[u]);
+        if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
             for (int u = 0; u < 4; u++) enqueue(p + u, pass[u]);
         }
     }
-    for (; p < e0a; p++) enqueue(p, aabb_pass(p));
-    for (; p + 2 <= e1; p += 2) {
-        const bool p0 = box_pass(p), p1 = box_pass(p + 1);
-        if (__any_sync(0xffffffffu, p0 | p1)) { enqueue(p, p0); enqueue(p + 1, p1); }
+    for (; p < e0a; p++) {
+        bool pass[K];
+        aabb_pass(p, pass);
+        enqueue(p, pass);
     }
-    for (; p < e1; p++) enqueue(p, box_pass(p));
+    for (; p + 2 <= e1; p += 2) {
+        bool p0[K], p1[K];
+        const bool any = box_pass(p, p0) | box_pass(p + 1, p1);
+        if (__any_sync(0xffffffffu, any)) { enqueue(p, p0); enqueue(p + 1, p1); }
+    }
+    for (; p < e1; p++) {
+        bool pass[K];
+        box_pass(p, pass);
+        enqueue(p, pass);
+    }
     (void)e2; /* the moving partners were voted on by k_wave_fk */
     ws.publish(lane); /* the grid walk below appends lane by lane, through the shared counter */
-    if (G.r_on && live) { /* one run of candidates: everything a geometry centred in this cell could touch */
-        const float fx = (ca.x - G.r_ox) * G.r_inv_h, fy = (ca.y - G.r_oy) * G.r_inv_h, fz = (ca.z - G.r_oz) * G.r_inv_h;
+#pragma unroll
+    for (int k = 0; k < K; k++)
+    if (G.r_on && live[k]) { /* one run of candidates: everything a geometry centred in this cell could touch */
+        const Vec3<float> c = ca[k];
+        const float fx = (c.x - G.r_ox) * G.r_inv_h, fy = (c.y - G.r_oy) * G.r_inv_h, fz = (c.z - G.r_oz) * G.r_inv_h;
         const int ix = (int)floorf(fx), iy = (int)floorf(fy), iz = (int)floorf(fz);
         if (ix >= 0 && iy >= 0 && iz >= 0 && ix < G.r_nx && iy < G.r_ny && iz < G.r_nz) {
             const int cell = (iz * G.r_ny + iy) * G.r_nx + ix;
             /* the query centre relative to the cell centre, like the entries */
-            const float qx = ca.x - (G.r_ox + ((float)ix + 0.5f) * G.r_h), qy = ca.y - (G.r_oy + ((float)iy + 0.5f) * G.r_h),
-                        qz = ca.z - (G.r_oz + ((float)iz + 0.5f) * G.r_h);
+            const float qx = c.x - (G.r_ox + ((float)ix + 0.5f) * G.r_h), qy = c.y - (G.r_oy + ((float)iy + 0.5f) * G.r_h),
+                        qz = c.z - (G.r_oz + ((float)iz + 0.5f) * G.r_h);
             const uint32_t *live_row = G.live + (size_t)a * G.wps;
             const int k1 = G.r_start[cell + 1];
-            for (int k = G.r_start[cell]; k < k1; k++) {
-                const uint2 e = G.r_c[k];
+            for (int kk = G.r_start[cell]; kk < k1; kk++) {
+                const uint2 e = G.r_c[kk];
                 const float2 xy = __half22float2(*reinterpret_cast<const __half2 *>(&e.x));
                 const float2 zr = __half22float2(*reinterpret_cast<const __half2 *>(&e.y));
                 const float dx = xy.x - qx, dy = xy.y - qy, dz = zr.x - qz;
                 const float reach = ra + zr.y;
                 if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
-                const int b = G.r_id[k]; /* rare from here on */
+                const int b = G.r_id[kk]; /* rare from here on */
                 if (!((live_row[b >> 5] >> (b & 31)) & 1u)) continue;
-                ws.put(w, unc, atomicAdd(&cnt[warp], 1u), s, a, b, 1);
+                ws.put(w, unc, atomicAdd(&cnt[warp], 1u), s[k], a, b, 1);
             }
         }
     }
-    WaveStage::flush_cta(w, unc, (const uint2 *)smem, cnt, &s_base, tid);
+    WaveStage::flush_cta(w, unc, (const uint2 *)smem, cnt, &s_base, tid, STAGE);
     (void)id_base;
 }
 
