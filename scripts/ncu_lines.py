@@ -28,3 +28,6 @@ ti, ts = sum(inst.values()) or 1, sum(samp.values()) or 1
 print(f"total warp instructions {ti}, stall samples {ts}")
 for k, v in samp.most_common(top):
     print(f"{100*v/ts:5.1f}% samples {100*inst[k]/ti:5.1f}% inst  {k[0]}:{k[1]}  {text[k]}")
+print("-- by instructions executed")
+for k, v in inst.most_common(top):
+    print(f"{100*v/ti:5.1f}% inst {100*samp[k]/ts:5.1f}% samples  {k[0]}:{k[1]}  {text[k]}")

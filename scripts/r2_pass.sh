@@ -17,7 +17,7 @@ if [[ $ST == *r* ]]; then
   timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err; echo "ref rc $?"
 fi
 if [[ $ST == *l* ]]; then
-  for WL in configs edges blocks clutter; do
+  for WL in configs edges clutter; do
     CMD="python bench.py --steps 2 --warmup 3 --no-cpu --workload $WL"
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
       --log-file $O/${T}_${WL}_launches.csv $CMD > $O/${T}_${WL}_ncu_launches.log 2>&1; echo "launches $WL rc $?"
@@ -42,6 +42,6 @@ if [[ $ST == *f* ]]; then
   for K in k_wave_fk; do python scripts/ncu_lines.py $O/${T}_configs_main.ncu-rep $K 14 > $O/${T}_lines_$K.txt 2>&1; done
   for K in k_mesh_tasks k_tri_items; do python scripts/ncu_lines.py $O/${T}_configs_tail.ncu-rep $K 14 > $O/${T}_lines_$K.txt 2>&1; done
   python scripts/ncu_lines.py $O/${T}_edges.ncu-rep k_states_tile 14 > $O/${T}_lines_k_states_tile.txt 2>&1
-  rm -f $O/${T}_clutter.ncu-rep $O/${T}_edges.ncu-rep $O/${T}_edges_heavy.ncu-rep
+  rm -f $O/${T}_*.ncu-rep   # the summaries travel back, the reports (60+ MB) do not
 fi
 du -sm $O; ls -la $O | tail -n 40

@@ -475,6 +475,8 @@ static void build_geoms(struct aa_rx_cl *cl) {
             if (!mesh->compiled) {
                 HostMesh *hm = new HostMesh();
                 mesh_compile(mesh, *hm);
+                /* k_mesh_tasks packs (item slot, node or triangle index) into one word: 24 bits of index */
+                if (hm->nodes.size() >= (size_t(1) << 24) || hm->tris.size() / 9 >= (size_t(1) << 24)) tmk_die("mesh: more than 2^24 triangles");
                 mesh->compiled = hm;
             }
             hmesh[m] = (const HostMesh *)mesh->compiled;

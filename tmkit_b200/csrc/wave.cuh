@@ -80,6 +80,7 @@ struct WaveStage {
     /* the same with the pair's queue key ready (Image::t_keys) */
     __device__ __forceinline__ void vote_key(const WaveBuf &w, const UncList &unc, bool pass, uint32_t s, uint32_t key, int lane) {
         const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m == 0u) return; /* warp-uniform: most votes of a group that had a survivor somewhere are empty */
         if (pass) put_key(w, unc, fill + __popc(m & ((1u << lane) - 1u)), s, key);
         fill += __popc(m);
     }
