@@ -1255,7 +1255,11 @@ static void launch_heavy(const Image<float> &f, const Src &src, const Sink &sink
     static const unsigned trav_ctas = getenv("TMK_TRAV_CTAS") ? (unsigned)atoi(getenv("TMK_TRAV_CTAS")) : (mode == 1 ? 7u : 6u);
     if (mode == 2) k_mesh_traverse_simple<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
     else if (mode == 1) k_mesh_traverse<Src, Sink><<<148 * trav_ctas, 128, 0, s>>>(f, src, sink, u, trav_next);
-    else k_mesh_tasks<Src, Sink><<<148 * trav_ctas, 128, 0, s>>>(f, src, sink, u, trav_next);
+    else {
+        uint32_t task_cap = TMK_TASK_NQ;
+        if (const char *e = getenv("TMK_TASK_CAP")) task_cap = (uint32_t)std::max(32, atoi(e)); /* test aid: the overflow path of k_mesh_tasks */
+        k_mesh_tasks<Src, Sink><<<148 * trav_ctas, 128, 0, s>>>(f, src, sink, u, trav_next, task_cap);
+    }
     CK(cudaGetLastError());
     k_tri_items<Src, Sink><<<ctas, 128, 0, s>>>(f, src, sink, u);
     CK(cudaGetLastError());
@@ -1296,8 +1300,6 @@ static UncList unc_list(struct aa_rx_cl *cl, size_t n_states, cudaStream_t s, bo
     u.tri_items = (uint2 *)b_tri.p;
     u.tri_n = (uint32_t *)b_cnt.p + 6;
     u.tile_ctr = (uint32_t *)b_cnt.p + 26; /* words 26, 27 */
-    u.task_cap = TMK_TASK_NQ;
-    if (const char *e = getenv("TMK_TASK_CAP")) u.task_cap = (uint32_t)std::max(32, atoi(e)); /* test aid: the overflow path of k_mesh_tasks */
     if (reset) CK(cudaMemsetAsync(b_cnt.p, 0, 512, s)); /* after every allocation: capturable */
     return u;
 }

@@ -100,7 +100,6 @@ struct UncList {
     uint32_t *tri_n;
     uint32_t tri_cap;
     uint32_t *tile_ctr; /* [0] next tile of the running k_states_tile launch, [1] CTAs that finished it */
-    uint32_t task_cap;  /* k_mesh_tasks: entries of a warp's task stacks it may use (<= TMK_TASK_TQ; test aid, forces the overflow path) */
 };
 #define TMK_MESH_REC 5 /* float4 per exported mesh item: (id_x, id_y, key, -) poseA[7] - poseB[7] - */
 #define TMK_WHOLE_PAIR 0xffffffffu
@@ -496,6 +495,29 @@ k_states_tile(Image<float> im, TileCfg cfg, Src src, Sink sink, UncList unc, uns
                         const float ez = fmaxf(fabsf(dx * z4.x + dy * z4.y + dz * z4.z) - z4.w, 0.f);
                         return live && ex * ex + ey * ey + ez * ez <= ra * ra;
                     };
+                    /* boxes aligned with the world axes come first in the segment: centre + half extents (Image::ab4,
+                     * read through L1: a warp-uniform 16-byte load), half the arithmetic of the oriented test */
+                    {
+                        const float4 *AB4 = (const float4 *)im.ab4;
+                        const float ra2 = ra * ra;
+                        auto aabb_pass = [&](int pp) {
+                            const float4 c4 = AB4[2 * pp], h4 = AB4[2 * pp + 1];
+                            const float ex = fmaxf(fabsf(c4.x - ca.x) - h4.x, 0.f), ey = fmaxf(fabsf(c4.y - ca.y) - h4.y, 0.f),
+                                        ez = fmaxf(fabsf(c4.z - ca.z) - h4.z, 0.f);
+                            return live && ex * ex + ey * ey + ez * ez <= ra2;
+                        };
+                        const int e0a = im.pa_aabb[a];
+                        for (; p + 4 <= e0a; p += 4) {
+                            bool pass[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) pass[u] = aabb_pass(p + u);
+                            if (__any_sync(0xffffffffu, pass[0] | pass[1] | pass[2] | pass[3])) {
+#pragma unroll
+                                for (int u = 0; u < 4; u++) enqueue(p + u, pass[u]);
+                            }
+                        }
+                        for (; p < e0a; p++) enqueue(p, aabb_pass(p));
+                    }
                     for (; p + 2 <= e1; p += 2) {
                         const bool p0 = box_pass(p), p1 = box_pass(p + 1);
                         if (__any_sync(0xffffffffu, p0 | p1)) { enqueue(p, p0); enqueue(p + 1, p1); }
@@ -816,7 +838,7 @@ __global__ void __launch_bounds__(128) k_mesh_traverse(Image<float> im, Src src,
 #define TMK_TASK_TQ 320
 #define TMK_TASK_F 22 /* floats of a query: Rms 9, tms 3, c 3, extents 3, rad2, shape a b c */
 template <class Src, class Sink>
-__global__ void __launch_bounds__(128) k_mesh_tasks(Image<float> im, Src src, Sink sink, UncList unc, uint32_t *next) {
+__global__ void __launch_bounds__(128) k_mesh_tasks(Image<float> im, Src src, Sink sink, UncList unc, uint32_t *next, uint32_t task_cap) {
     __shared__ float s_f[4][TMK_TASK_F][32];
     __shared__ uint32_t s_i[4][6][32]; /* shape kind, mesh record, node pointer (2 words), triangle pointer (2 words) */
     __shared__ uint32_t s_nq[4][TMK_TASK_NQ];
@@ -829,7 +851,10 @@ __global__ void __launch_bounds__(128) k_mesh_tasks(Image<float> im, Src src, Si
     const unsigned lt = (1u << lane) - 1u;
     uint32_t n = *unc.mesh_n;
     if (n > unc.mesh_cap) n = unc.mesh_cap;
-    const int nq_cap = (int)min(unc.task_cap, (uint32_t)TMK_TASK_NQ), tq_cap = (int)min(unc.task_cap, (uint32_t)TMK_TASK_TQ);
+    /* task_cap: entries of a warp's task stacks it may use (test aid: a small value forces the overflow path).  Not a
+     * field of UncList: that struct is passed by value to a noinline function of the tile kernel, and one more word
+     * pushed it over the size the ABI passes in registers (tile kernel 93 -> 125 registers, 272 B of stack) */
+    const int nq_cap = (int)min(task_cap, (uint32_t)TMK_TASK_NQ), tq_cap = (int)min(task_cap, (uint32_t)TMK_TASK_TQ);
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) { base = atomicAdd(next, 32u); s_dead[warp] = 0u; }
