@@ -737,7 +737,7 @@ def run_workload(ctx: Ctx, args, workload: str, steps: int, warmup: int, cpu_bud
     achieved_tf = flops_unit * n_mine / (k_ms * 1e-3) / 1e12
     kernel = ("k_states_tile<SrcEdgeLevel> + k_heavy_mixed + k_edges_compact, all bisection levels" if edges
               else "wavefront pipeline k_wave_fk + k_wave_broad + k_wave_quick + k_wave_export + k_wave_bits, then the deferred "
-                   "narrowphase (k_conv_items beside k_mesh_traverse -> k_tri_items)")
+                   "narrowphase (k_conv_items beside k_mesh_tasks -> k_tri_items)")
     par = f"dp{world}: contiguous 1024-aligned slice per rank"
     if world > 1:
         par += (", one ncclAllGather of the validity words per step inside libtmkcl.so (aa_rx_cl_check_*_shard_dev), "
