@@ -1,25 +1,26 @@
-/* wave.cuh - the state-validity pipeline for LARGE scenes, wavefront style (BASELINE.json configs[4]: two arms,
- * 20 moving geometries, hundreds of static obstacles in a uniform grid).
+/* wave.cuh - the state-validity pipeline for configuration batches, wavefront style (BASELINE.json configs[1], [3],
+ * [4]: every batch of 4096 states or more; the swept-edge levels and small batches stay on the tile kernel).
  *
- * The tile kernel (pipeline.cuh) keeps every pose of a state in shared memory so that nothing touches HBM; with 20
- * moving geometries that slab is 143 KB per 256 states - one CTA of 8 warps per SM - and the lane-divergent grid
- * walk then runs with nothing to hide its latency behind (measured: 12.5 % of peak warps, issue slots 24 % busy,
- * 6.8 ms per 2^20 configurations).  For such scenes the arithmetic per state (~15 k instructions) dwarfs the bytes
- * of its poses (560 B), so here the phases are separate kernels that hand their data through HBM / L2 and each
- * runs at full occupancy:
+ * The tile kernel (pipeline.cuh) keeps every pose of a state in shared memory so that nothing touches HBM: two CTAs
+ * per SM for the 10 geometries of one arm (issue slots 53 % busy), one CTA for the 20 of two arms (24 %).  The
+ * arithmetic per state (~11 k instructions) dwarfs the bytes of its poses (280 - 560 B), so here the phases are
+ * separate kernels that hand their data through HBM / L2 and each runs at full occupancy:
  *
  *   k_wave_fk      one thread = one state: the joint chain in registers, every moving geometry's pose written to
- *                  planes [geom * 7 + k][state] (coalesced), hit flag cleared
- *   k_wave_broad   one thread = one (state, moving geometry); blockIdx.y is the geometry, so the partner lists are
- *                  CTA-uniform (broadcast loads); the small obstacles come from the reach list of the one grid cell
- *                  the geometry's centre lies in (a contiguous run of half-precision spheres, rounded
- *                  conservatively, read through L2); survivors are staged per warp in shared memory and flushed
- *                  with one atomic
+ *                  planes [geom * 7 + k][state] (coalesced), hit flag cleared, moving-moving pairs voted
+ *   k_wave_broad   one thread = K = 2 states of one moving geometry (a0 + blockIdx.y), so the partner lists are
+ *                  CTA-uniform (broadcast loads) and shared by the two tests of a pair: bounding spheres against a
+ *                  precomputed squared reach, world-aligned boxes as centre + half extents, oriented boxes exactly;
+ *                  the small obstacles of large scenes come from the reach list of the one grid cell the geometry's
+ *                  centre lies in (a contiguous run of half-precision spheres, rounded conservatively, read
+ *                  through L2); survivors are staged per warp in shared memory (the fill is a warp-uniform
+ *                  register) and flushed with one global atomic per CTA.  Run in stages over index ranges of the
+ *                  geometries, each followed by its k_wave_quick: a state a stage condemns skips the later ones
  *   k_wave_quick   one thread = one surviving (state, pair): quick certificates (dev_math.cuh quick_pair); HIT sets
  *                  the state's flag, undecided pairs go to a (state, pair) list, FP32-ambiguous ones to the exact
  *                  re-check list
  *   k_wave_export  one thread = one undecided pair of a state that is still not known to collide: the record the
- *                  deferred narrowphase kernels of pipeline.cuh consume (k_conv_items, k_mesh_traverse, ...)
+ *                  deferred narrowphase kernels of pipeline.cuh consume (k_conv_items, k_mesh_tasks, k_tri_items)
  *   k_wave_bits    one thread = one state: the validity words
  *
  * Verdicts are those of the tile kernel bit for bit: the same tests in the same arithmetic decide every pair.
