@@ -70,15 +70,10 @@ struct WaveStage {
             else *unc.overflow = 1u;
         }
     }
-    /* warp-uniform call: every lane votes, passing lanes get consecutive slots.  The warp's fill is a warp-uniform
+    /* warp-uniform calls: every lane votes, passing lanes get consecutive slots.  The warp's fill is a warp-uniform
      * register (every lane adds the same popc): no atomic, no shuffle; publish() stores it for the flush */
     uint32_t fill;
-    __device__ __forceinline__ void vote(const WaveBuf &w, const UncList &unc, bool pass, uint32_t s, int a, int b, int b_static, int lane) {
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) put(w, unc, fill + __popc(m & ((1u << lane) - 1u)), s, a, b, b_static);
-        fill += __popc(m);
-    }
-    /* the same with the pair's queue key ready (Image::t_keys) */
+    /* key: the pair's queue key, ready to store (Image::t_keys) */
     __device__ __forceinline__ void vote_key(const WaveBuf &w, const UncList &unc, bool pass, uint32_t s, uint32_t key, int lane) {
         const unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m == 0u) return; /* warp-uniform: most votes of a group that had a survivor somewhere are empty */
